@@ -1,0 +1,25 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """tests/golden/reference_golden.npz -> {case: {key: ndarray}} (outputs of the REAL
+    reference, produced by tests/golden/make_golden.py in the build container)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
+    cases = {}
+    for k in z.files:
+        c, name = k.split("/", 1)
+        cases.setdefault(c, {})[name] = z[k]
+    return cases

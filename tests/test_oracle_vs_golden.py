@@ -1,0 +1,100 @@
+"""CPU: the oracle (oracle/s2l_oracle.py) must reproduce the outputs of the real
+reference stored in tests/golden/reference_golden.npz (the reference
+has no KATs of its own, so the pin is the reference run in the build container)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import s2l_oracle as O
+from oracle import synth
+
+TOL = 2e-6   # fp32; differences only from BLAS blocking order ([N,..] vs broadcast shapes)
+
+
+def sd(kind, uv_dims=2, och=3):
+    return O.to_torch_sd(synth.make_state_dict(0, kind, uv_dims, och))
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+def test_audio_net(golden, kind):
+    g = golden["audio_%s" % kind]
+    out = O.audio_merge_forward(sd(kind), torch.from_numpy(g["audio"]))
+    np.testing.assert_allclose(out.numpy(), g["latent"], atol=TOL, rtol=0)
+    out2 = O.audio_merge_forward(sd(kind), torch.from_numpy(g["audio"]).permute(0, 2, 1).contiguous())
+    np.testing.assert_allclose(out2.numpy(), g["latent_from_29x16"], atol=TOL, rtol=0)
+    # synthetic audio generator is the one the golden was made with
+    np.testing.assert_array_equal(g["audio"], synth.make_audio(4, seed=1))
+
+
+def test_embedders_and_coords(golden):
+    g = golden["embed"]
+    np.testing.assert_array_equal(O.uv_embed(torch.from_numpy(g["uv"])).numpy(), g["pe"])
+    np.testing.assert_array_equal(O.time_embed(torch.tensor([5])).numpy(), g["t5"])
+    np.testing.assert_array_equal(O.time_embed(torch.tensor([6000])).numpy(), g["t6000"])
+    np.testing.assert_array_equal(O.get_coords(7, 5).numpy(), g["coords_7x5"])
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+@pytest.mark.parametrize("shape", [(24, 32, 5), (8, 8, 6000)])
+def test_plain(golden, kind, shape):
+    H, W, idx = shape
+    g = golden["plain_%s_%dx%d_i%d" % (kind, H, W, idx)]
+    for once in (True, False):
+        out = O.render_plain(sd(kind), torch.from_numpy(g["audio"]), idx, H, W, audio_once=once)
+        np.testing.assert_allclose(out.numpy(), g["rgb"], atol=TOL * 10 if kind == "kaiming" else TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+def test_rowlatent(golden, kind):
+    g = golden["rowlatent_%s" % kind]
+    out = O.rgb_forward(sd(kind), torch.from_numpy(g["x"]), torch.tensor([int(g["index"])]))
+    np.testing.assert_allclose(out.numpy(), g["out"], atol=TOL * 10 if kind == "kaiming" else TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+@pytest.mark.parametrize("seed", [11, 12])
+def test_ensemble4(golden, kind, seed):
+    g = golden["ens4_%s_seed%d" % (kind, seed)]
+    H, W = int(g["H"]), int(g["W"])
+    # RNG alignment: the reference drew eps as ry*rand(1)/2 right after manual_seed(seed)
+    torch.manual_seed(seed)
+    eps = (0.5 / H) * torch.rand(1) / 2.0
+    np.testing.assert_array_equal(eps.numpy(), g["eps"])
+    out = O.render_ensemble4(sd(kind), torch.from_numpy(g["audio"]), int(g["index"]), H, W, eps)
+    np.testing.assert_allclose(out.numpy(), g["rgb"], atol=TOL * 10 if kind == "kaiming" else TOL, rtol=0)
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+@pytest.mark.parametrize("shape", [(8, 8, 16), (6, 10, 64)])
+def test_volumetric(golden, kind, shape):
+    H, W, S = shape
+    g = golden["vol_%s_%dx%dx%d" % (kind, H, W, S)]
+    c2w = torch.from_numpy(g["c2w"])
+    ro, rd = O.get_rays(H, W, float(g["focal"]), c2w)
+    np.testing.assert_array_equal(ro.reshape(-1, 3).numpy(), g["rays_o"])
+    np.testing.assert_array_equal(rd.reshape(-1, 3).numpy(), g["rays_d"])
+    rgb, weights, depth, raw = O.render_volumetric(sd(kind, 3, 4), torch.from_numpy(g["audio"]), int(g["index"]),
+                                                   H, W, S, float(g["focal"]), c2w, return_aux=True)
+    tol = TOL * 10 if kind == "kaiming" else TOL
+    np.testing.assert_allclose(raw.numpy(), g["raw"], atol=tol, rtol=0)
+    np.testing.assert_allclose(rgb.numpy(), g["rgb"], atol=tol, rtol=0)
+    np.testing.assert_allclose(weights.numpy(), g["weights"], atol=tol, rtol=0)
+    np.testing.assert_allclose(depth.numpy(), g["depth"], atol=tol, rtol=0)
+
+
+def test_composite_only(golden):
+    g = golden["composite_only"]
+    rgb, w, d = O.density2outputs(torch.from_numpy(g["raw"]), torch.from_numpy(g["z"]), torch.from_numpy(g["rays_d"]))
+    np.testing.assert_array_equal(rgb.numpy(), g["rgb"])
+    np.testing.assert_array_equal(w.numpy(), g["weights"])
+    np.testing.assert_array_equal(d.numpy(), g["depth"])
+    # property: weights are a sub-probability along the ray
+    assert (w.sum(-1) <= 1 + 1e-5).all() and (w >= 0).all()
+
+
+def test_fp64_truth_close_to_fp32_reference(golden):
+    """the float64 oracle is the 'truth' used to rank errors; it must sit within fp32 noise of the reference."""
+    g = golden["plain_kaiming_24x32_i5"]
+    sd64 = O.to_torch_sd(synth.make_state_dict(0, "kaiming"), torch.float64)
+    out = O.render_plain(sd64, torch.from_numpy(g["audio"]).double(), 5, 24, 32)
+    assert np.abs(out.numpy() - g["rgb"]).max() < 2e-4
