@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — lip frames/s of the Speech2Lip rendering hot path on B200.
+
+Default workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+    volumetric mode, 256x256 rays, 64 samples/ray, batch = 8 frames per step, 1 GPU,
+    parity arithmetic (tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate).
+A "step" = one pass of the whole path (AudioNet -> per-frame biases -> ray generation -> fused MLP ->
+alpha compositing) over one batch of 8 synthetic frames.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same through the public
+API with host buffers (H2D of the windows/poses and D2H of the frames inside the timed region),
+`roofline` = achieved algorithmic FLOP/s of the fused-MLP kernel vs the measured bf16 tensor peak,
+`cpu_baseline` = the oracle timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_POINT = {"volumetric": 1_246_208, "plain": 1_224_192, "ensemble4": 1_224_192}   # SURVEY §8(d), algorithmic
+METRIC = "lip frames/sec @256x256,64 samples/ray"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="volumetric", choices=["volumetric", "plain", "ensemble4"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16x1", "fp32"])
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    if a.mode == "volumetric":
+        return "volumetric %dx%d rays x %d samples/ray, %d frames/step/GPU (BASELINE configs[1])" % (a.size, a.size, a.samples, a.frames)
+    return "%s %dx%d, %d frames/step/GPU" % (a.mode, a.size, a.size, a.frames)
+
+
+def points_per_frame(a):
+    n = a.size * a.size
+    return n * (a.samples if a.mode == "volumetric" else 4 if a.mode == "ensemble4" else 1)
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(a, threads):
+    """Times the oracle port (reference arithmetic, torch CPU fp32, no_grad) on a bounded sample of the
+    workload and extrapolates to frames/s.  Sample = `cpu_rays` rays (x samples) of one frame, including
+    AudioNet once and compositing — i.e. cpu_rays/(size*size) of a frame."""
+    from oracle import s2l_oracle as O
+    from oracle import synth
+    torch.set_num_threads(threads)
+    H = W = a.size
+    audio = torch.from_numpy(synth.make_audio(1, seed=1))
+    if a.mode == "volumetric":
+        sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming", 3, 4))
+        ro, rd = O.get_rays(H, W, 1200.0, torch.eye(4)[:3])
+        n = min(a.cpu_rays, H * W)
+        ro, rd = ro.reshape(-1, 3)[:n], rd.reshape(-1, 3)[:n]
+        z = O.z_samples(a.samples)
+
+        def run():
+            with torch.no_grad():
+                lat = O.audio_merge_forward(sd, audio)
+                pts = (ro[:, None, :] + rd[:, None, :] * z[None, :, None]).reshape(-1, 3)
+                outs = []
+                for s in range(0, pts.shape[0], 65536):
+                    p = pts[s:s + 65536]
+                    outs.append(O.rgb_forward(sd, torch.cat([p, lat.expand(p.shape[0], -1)], -1), torch.tensor([0]), uv_dims=3))
+                raw = torch.cat(outs).reshape(n, a.samples, 4)
+                return O.density2outputs(raw, z.expand(n, a.samples), rd)[0]
+        frac = n / float(H * W)
+        desc = "%d of %d rays x %d samples of one frame (AudioNet once + MLP in 65536-point chunks + compositing)" % (n, H * W, a.samples)
+    else:
+        sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming", 2, 3))
+        n_rows = max(1, min(H, a.cpu_rays // W))
+
+        def run():
+            with torch.no_grad():
+                if a.mode == "plain":
+                    return O.render_plain(sd, audio, 0, n_rows, W)
+                return O.render_ensemble4(sd, audio, 0, n_rows, W, 0.0)
+        frac = n_rows / float(H)
+        desc = "%d of %d pixel rows of one frame, mode %s" % (n_rows, H, a.mode)
+    return run, frac, desc
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    run, frac, desc = cpu_sample(a, threads)
+    for _ in range(max(1, min(a.warmup, 2))):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run()
+    dt = (time.perf_counter() - t0) / a.steps
+    fps = frac / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "reference_arm": "oracle port of the reference's PyTorch CPU path "
+                   "(the reference is pure Python with no installable package; /root/reference is absent on this box)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "each step = " + desc + "; frames/s extrapolated by the sampled fraction"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for (t, l) in self.samples if t_begin <= t <= t_end] or [l.split(", ") for (_, l) in self.samples[-3:]]
+        sm, reasons, mx, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(a):
+    import ctypes as C
+    import torch.distributed as dist
+    import speech2lip_b200 as s2l
+    from speech2lip_b200 import _cabi, renderer as R
+    from speech2lip_b200.dist import broadcast_params
+    from oracle import synth            # synthetic weights/inputs only (no oracle compute on this path)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    vol = a.mode == "volumetric"
+    uvd, och = (3, 4) if vol else (2, 3)
+    H = W = a.size
+    F = a.frames
+    # weights: rank 0 owns them, everyone else receives ONE broadcast; then zero communication
+    sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0 if rank == 0 else 1000 + rank, "kaiming", uvd, och).items()}
+    if world > 1:
+        broadcast_params(sd, src=0)
+    w = s2l.PackedWeights(sd, uvd, och)
+    rend = s2l.LipRenderer(w, a.precision)
+    lib = _cabi.lib()
+
+    # per-rank frames (weak scaling: F frames per GPU per step), host-resident pinned inputs for the e2e leg
+    audio_h = torch.from_numpy(synth.make_audio(F, seed=100 + rank)).pin_memory()
+    index_h = (torch.arange(F, dtype=torch.int64) + rank * F).pin_memory()
+    c2w_h = torch.eye(4)[:3].contiguous().pin_memory()
+    out_h = torch.empty(F, H, W, 3, pin_memory=True)
+    audio_d, index_d, c2w_d = audio_h.to(dev), index_h.to(dev), c2w_h.to(dev)
+    z_d = torch.linspace(0., 1., a.samples, device=dev) if vol else None
+    rgb_d = torch.empty(F, H, W, 3, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    geom = _cabi.S2LGeom(n_frames=F, height=H, width=W, n_samples=a.samples if vol else 0,
+                         pts_mode={"volumetric": _cabi.PTS_RAYS, "plain": _cabi.PTS_GRID, "ensemble4": _cabi.PTS_GRID_ENS4}[a.mode],
+                         uv_dims=uvd, out_ch=och, z_per_ray=0, rays_per_frame_shared=1, pts_per_frame=0, eps_shift=0.001)
+    P = points_per_frame(a)
+    bias_d = torch.empty(F, 4, 256, device=dev)
+    raw_d = rgb_d if a.mode == "plain" else torch.empty(F * P * och, device=dev)
+    ro_d = torch.empty(H, W, 3, device=dev)
+    rd_d = torch.empty(H, W, 3, device=dev)
+    prec = _cabi.PRECISIONS[a.precision]
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = R._ptr
+
+    def step_device(ev=None):
+        """the decomposed whole-path call (identical kernels to s2l_render_frames) with events around the fused MLP"""
+        if vol:
+            _cabi.check(lib.s2l_get_rays(p(c2w_d), H, W, 1200.0, p(ro_d), p(rd_d), st()), "get_rays")
+        _cabi.check(lib.s2l_audio_encode_fwd(p(w.blob), p(audio_d), 0, p(index_d), None, p(bias_d), F, uvd, och, st()), "audio")
+        if ev:
+            ev[0].record()
+        _cabi.check(lib.s2l_mlp_fwd(p(w.blob), C.byref(geom), p(bias_d), None, p(ro_d) if vol else None, p(rd_d) if vol else None,
+                                    p(z_d), p(raw_d), prec, st()), "mlp")
+        if ev:
+            ev[1].record()
+        if vol:
+            _cabi.check(lib.s2l_composite_fwd(p(raw_d), p(z_d), 0, p(rd_d), H * W * F, H * W, a.samples, p(rgb_d), None, None, st()), "composite")
+        elif a.mode == "ensemble4":
+            _cabi.check(lib.s2l_ensemble4_blend(p(raw_d), C.byref(geom), p(rgb_d), st()), "blend")
+
+    def step_e2e():
+        """public API on HOST buffers: H2D (windows, indices, pose) -> render -> D2H (frames), all on the current stream"""
+        ad = audio_h.to(dev, non_blocking=True)
+        idd = index_h.to(dev, non_blocking=True)
+        if vol:
+            cd = c2w_h.to(dev, non_blocking=True)
+            ro, rd = R.get_rays(H, W, 1200.0, cd)
+            rgb = rend.render_frames(ad, idd, H, W, mode="volumetric", rays_o=ro, rays_d=rd, z_vals=z_d, out=rgb_d)
+        else:
+            rgb = rend.render_frames(ad, idd, H, W, mode=a.mode, eps_shift=0.001, out=rgb_d)
+        out_h.copy_(rgb, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_kernel_events):
+        tot = 0.0
+        ker = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                                    # evict L2 between timed iterations (untimed)
+            e0, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] if with_kernel_events else None
+            e0.record()
+            fn(ev) if with_kernel_events else fn()
+            e3.record()
+            e3.synchronize()
+            tot += e0.elapsed_time(e3)
+            if ev:
+                ker += ev[0].elapsed_time(ev[1])
+        return tot, ker
+
+    # ---- warm-up (untimed), then the timed region bracketed by barrier + synchronize
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+        step_e2e()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib.s2l_launch_count(1)
+    t_begin = time.perf_counter()
+    barrier()
+    dev_ms, ker_ms = timed(step_device, a.steps, True)
+    barrier()
+    launches = lib.s2l_launch_count(0)
+    e2e_ms, _ = timed(step_e2e, a.steps, False)
+    barrier()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms, ker_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, ker_ms = [float(x) for x in t.tolist()]
+    checksum = float(rgb_d.double().sum().item())
+    finite = bool(torch.isfinite(rgb_d).all().item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        tensor_bound = a.precision != "fp32"
+        if tensor_bound:
+            peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1590 (B200_PROFILING.md)"
+            peak = peak or 1590.0
+        else:
+            peak, peak_src = 72.0, "nominal fp32 FFMA peak 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 figure)"
+        flop_launch = float(F) * P * FLOP_PER_POINT[a.mode]
+        ach = flop_launch / (ker_ms / a.steps * 1e-3) / 1e12
+        frames_total = F * world * a.steps
+        line = {
+            "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": {"bf16x3": "bf16x3-split (fp32 accumulate)", "bf16x1": "bf16", "fp32": "f32"}[a.precision], "data": "synthetic",
+            "config": {"workload": workload_name(a), "mode": a.mode, "precision": a.precision,
+                       "points_per_frame": P, "weights": "synthetic kaiming-normal ('trained-like'), seed 0",
+                       "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
+                       "parallelism": "frames sharded across ranks, 1 NCCL weight broadcast at start, none during render"},
+            "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(audio_h.numel() * 4 + index_h.numel() * 8 + (48 if vol else 0)),
+                    "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor" if tensor_bound else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": None, "kernel": "mlp_tc_kernel" if tensor_bound else "mlp_fp32_kernel",
+                         "kernel_ms_per_launch": ker_ms / a.steps, "flop_per_point_algorithmic": FLOP_PER_POINT[a.mode],
+                         "mma_multiplier": 3 if a.precision == "bf16x3" else 1, "peak_source": peak_src,
+                         "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None},
+            "clocks": clocks, "checksum": checksum, "finite": finite,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            run, frac, desc = cpu_sample(a, threads)
+            run()
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 3 and (reps == 0 or time.perf_counter() - t0 < 20.0):
+                run()
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": frac / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": desc + "; %d repetitions, frames/s extrapolated by the sampled fraction" % reps}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/*
+ * speech2lip_b200 — C ABI of the B200-native Speech2Lip rendering hot path.
+ *
+ * The reference (CVMI-Lab/Speech2Lip) is pure Python/PyTorch and has no FFI of its
+ * own; its boundary for this path is the Python class
+ *   src/face_simple/models/tf_nerf.py:12  class TalkingFace(nn.Module)
+ * called by inference.py:144-159 and src/face_simple/training.py:158-251.
+ * The entry points below are what a ctypes binding for that class binds
+ * (speech2lip_b200/_cabi.py is that binding; INTEGRATION.md shows the reference-side stub).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a *device* pointer borrowed
+ *    from the caller (torch owns the memory) unless the name ends in _host.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all
+ *    work is enqueued on it, no hidden synchronisation, no allocation.
+ *  - return value: 0 on success, non-zero on error; s2l_last_error() returns a
+ *    thread-local, NUL-terminated description of the last failure.
+ *  - all floating-point tensors are fp32, row-major, contiguous.
+ */
+#ifndef SPEECH2LIP_B200_H
+#define SPEECH2LIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2L_ABI_VERSION 1
+
+/* Number of parameter tensors s2l_pack_weights() reads, in this fixed order
+ * (reference state_dict names, tf_nerf.py:85-172):                                  */
+enum {
+  S2L_P_CONV0_W = 0, S2L_P_CONV0_B,      /* encoder_conv.0  [32,29,3],[32]   tf_nerf.py:92  */
+  S2L_P_CONV1_W, S2L_P_CONV1_B,          /* encoder_conv.2  [32,32,3],[32]   tf_nerf.py:95  */
+  S2L_P_CONV2_W, S2L_P_CONV2_B,          /* encoder_conv.4  [64,32,3],[64]   tf_nerf.py:98  */
+  S2L_P_CONV3_W, S2L_P_CONV3_B,          /* encoder_conv.6  [64,64,3],[64]   tf_nerf.py:101 */
+  S2L_P_FC1_W, S2L_P_FC1_B,              /* encoder_fc1.0   [64,64],[64]     tf_nerf.py:106 */
+  S2L_P_FC2_W, S2L_P_FC2_B,              /* encoder_fc1.2   [64,64],[64]     tf_nerf.py:108 */
+  S2L_P_FC_UV_W, S2L_P_FC_UV_B,          /* fc_uv           [256,E],[256]    tf_nerf.py:149 */
+  S2L_P_FC_UV_SKIP_W, S2L_P_FC_UV_SKIP_B,/* fc_uv_skip      [256,E],[256]    tf_nerf.py:150 */
+  S2L_P_FC_AUDIO_W, S2L_P_FC_AUDIO_B,    /* fc_audio        [256,64],[256]   tf_nerf.py:152 */
+  S2L_P_FC_AUDIO_SKIP_W, S2L_P_FC_AUDIO_SKIP_B, /* fc_audio_skip             tf_nerf.py:153 */
+  S2L_P_FC_TIME_W, S2L_P_FC_TIME_B,      /* fc_time         [256,20],[256]   tf_nerf.py:159 */
+  S2L_P_FC_TIME_SKIP_W, S2L_P_FC_TIME_SKIP_B,   /* fc_time_skip              tf_nerf.py:160 */
+  S2L_P_PTS0_W, S2L_P_PTS0_B,            /* pts_linears.0..7 [256,256] ([256,512] for .5, input
+                                            order [h_skip,h])                tf_nerf.py:170-172 */
+  S2L_P_PTS_LAST_B = S2L_P_PTS0_W + 15,
+  S2L_P_OUT_W, S2L_P_OUT_B,              /* output_linear   [out_ch,256],[out_ch] tf_nerf.py:144 */
+  S2L_NUM_PARAMS
+};
+
+/* MLP arithmetic selection for s2l_mlp_fwd / s2l_render_frames. */
+enum {
+  S2L_PREC_FP32   = 0,  /* CUDA-core fp32 FFMA, literal (unfolded) layer order: the exact path      */
+  S2L_PREC_BF16X3 = 1,  /* tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (parity)   */
+  S2L_PREC_BF16X1 = 2   /* tcgen05 single bf16 pass (fast, NOT within the 1e-3 parity bar)          */
+};
+
+/* How the kernel obtains the coordinates of point-evaluation p of frame f. */
+enum {
+  S2L_PTS_GRID      = 0, /* (u,v) = get_coords(W,H) grid, 1 eval / pixel      rendering.py:9-28, inference.py:146 */
+  S2L_PTS_GRID_ENS4 = 1, /* 4 jittered+clamped taps / pixel, tap-minor order  training.py:195-236                 */
+  S2L_PTS_RAYS      = 2, /* x = o + d*z, S samples / ray, sample-minor order  (volumetric mode)      */
+  S2L_PTS_EXPLICIT  = 3  /* coordinates read from `pts` [F*P, uv_dims]         rgb_forward contract, tf_nerf.py:225 */
+};
+
+typedef struct S2LGeom {
+  int32_t n_frames;        /* F                                                              */
+  int32_t height, width;   /* H, W (GRID*, RAYS: rays per frame = H*W)                        */
+  int32_t n_samples;       /* S for RAYS, else ignored                                        */
+  int32_t pts_mode;        /* S2L_PTS_*                                                       */
+  int32_t uv_dims;         /* 2 (live model) or 3 (volumetric model), must match the blob     */
+  int32_t out_ch;          /* 3 or 4, must match the blob                                     */
+  int32_t z_per_ray;       /* RAYS: 1 -> z_vals is [F*R,S]; 0 -> z_vals is [S] shared         */
+  int32_t rays_per_frame_shared; /* RAYS: 1 -> rays_o/rays_d are [R,3] shared by all frames;
+                                           0 -> [F*R,3]                                       */
+  int64_t pts_per_frame;   /* EXPLICIT: P (points per frame); otherwise derived               */
+  float   eps_shift;       /* GRID_ENS4: the reference's eps_shift draw (training.py:200)     */
+} S2LGeom;
+
+/* Thread-local description of the last error (never NULL). */
+const char* s2l_last_error(void);
+int32_t     s2l_abi_version(void);
+
+/* PositionalEncodingTime.div_term (tf_nerf.py:431-432), 10 fp32 values, host-side helper. */
+void s2l_time_div_term(float* out10_host);
+
+/* Size in bytes of the packed weight blob for a model with the given dims. */
+size_t s2l_blob_bytes(int32_t uv_dims, int32_t out_ch);
+
+/* Replaces: TalkingFace.__init__ parameter set + load_state_dict (tf_nerf.py:13-195,
+ * src/checkpoints.py:97-116).  `params` is a HOST array of S2L_NUM_PARAMS DEVICE pointers
+ * (fp32, PyTorch [out,in] layout).  Writes the kernel-layout blob (fp32 exact-path copies,
+ * folded/split bf16 tensor-core operand images, constant tables).  Must be re-run whenever a
+ * parameter changes (optimizer.step, load_state_dict). */
+int32_t s2l_pack_weights(const float* const* params_host, void* blob, int32_t uv_dims, int32_t out_ch,
+                         void* stream);
+
+/* Replaces: TalkingFace.audio_merge_forward (tf_nerf.py:197-213) plus the per-frame-constant
+ * terms of rgb_forward (fc_audio/fc_time and their *_skip twins, tf_nerf.py:254-258,270-276) and
+ * PositionalEncodingTime (tf_nerf.py:427-442).
+ *   audio      [F,16,29] (transposed=0) or [F,29,16] (transposed=1)
+ *   frame_idx  [F] int64 (time_pts; NULL -> time term omitted)
+ *   latent     [F,64]  out (may be NULL)
+ *   frame_bias [F,4,256] out (may be NULL): rows = {bias0, bias_skip, folded bias0', folded bias5'} */
+int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, int32_t transposed,
+                             const int64_t* frame_idx, float* latent, float* frame_bias,
+                             int32_t n_frames, int32_t uv_dims, int32_t out_ch, void* stream);
+
+/* Replaces: TalkingFace.rgb_forward (tf_nerf.py:225-285) for F frames x P points with a
+ * per-frame-constant latent (frame_bias from s2l_audio_encode_fwd).  Point coordinates come from
+ * geom->pts_mode.  raw_out [F*P_padless, out_ch] receives the raw linear outputs in point order. */
+int32_t s2l_mlp_fwd(const void* blob, const S2LGeom* geom, const float* frame_bias,
+                    const float* pts, const float* rays_o, const float* rays_d, const float* z_vals,
+                    float* raw_out, int32_t precision, void* stream);
+
+/* Replaces: TalkingFace.rgb_forward for the general contract (arbitrary latent per row):
+ *   x [N, uv_dims+64], time index `time_idx` (position[0], tf_nerf.py:439) -> out [N,out_ch].
+ * Always fp32 exact path. */
+int32_t s2l_rgb_forward_rows(const void* blob, const float* x, int64_t n_rows, int64_t time_idx,
+                             int32_t has_time, float* out, int32_t uv_dims, int32_t out_ch, void* stream);
+
+/* Replaces: the 4-tap blend of Trainer.predict_lip_image (training.py:238-249).
+ *   raw [F*H*W*4, out_ch] (tap-minor) -> rgb [F,H,W,3] */
+int32_t s2l_ensemble4_blend(const float* raw, const S2LGeom* geom, float* rgb, void* stream);
+
+/* Replaces: density2outputs (rendering.py:30-62, raw_noise_std=0).
+ *   raw [R,S,4], z_vals ([R,S] or [S]), rays_d [R,3] -> rgb [R,3], weights [R,S] (NULL ok), depth [R] (NULL ok).
+ *   rays_mod: rays_d row index = ray % rays_mod (rays shared between frames), 0 = no wrap. */
+int32_t s2l_composite_fwd(const float* raw, const float* z_vals, int32_t z_per_ray, const float* rays_d,
+                          int64_t n_rays, int64_t rays_mod, int32_t n_samples,
+                          float* rgb, float* weights, float* depth, void* stream);
+
+/* Replaces: get_rays (src/common.py:12-21).  c2w [3,4] row-major (device) -> rays_o, rays_d [H*W,3]. */
+int32_t s2l_get_rays(const float* c2w, int32_t height, int32_t width, float focal,
+                     float* rays_o, float* rays_d, void* stream);
+
+/* Whole-path call on device buffers: AudioNet -> MLP -> per-pixel reduction for F frames.
+ *   rgb [F,H,W,3] out; scratch must hold s2l_render_scratch_bytes(geom) bytes.
+ * Replaces the loop body of inference.py:144-159 (GRID), training.py:158-251 (GRID_ENS4) or the
+ * assembled volumetric path (RAYS). */
+size_t  s2l_render_scratch_bytes(const S2LGeom* geom);
+int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, const float* audio, const int64_t* frame_idx,
+                          const float* rays_o, const float* rays_d, const float* z_vals,
+                          float* rgb, float* weights, float* depth, void* scratch, int32_t precision,
+                          void* stream);
+
+/* Number of kernels of this library launched by this thread since the last reset (bench "gpu_launches"). */
+int64_t s2l_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECH2LIP_B200_H */

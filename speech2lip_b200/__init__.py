@@ -1,0 +1,10 @@
+"""speech2lip_b200 — B200-native (sm_100a) implementation of the Speech2Lip per-frame rendering hot path:
+AudioNet + the canonical-space implicit MLP renderer of src/face_simple, behind the reference's own
+TalkingFace interface.  See DESIGN.md / INTEGRATION.md."""
+from ._cabi import LIB_PATH, PARAM_NAMES  # noqa: F401
+from .renderer import (LipRenderer, PackedWeights, audio_encode, density2outputs, get_rays, mlp_points,  # noqa: F401
+                       rgb_forward_rows)
+from .talking_face import TalkingFace  # noqa: F401
+
+__all__ = ["TalkingFace", "LipRenderer", "PackedWeights", "audio_encode", "rgb_forward_rows", "mlp_points",
+           "density2outputs", "get_rays", "LIB_PATH", "PARAM_NAMES"]

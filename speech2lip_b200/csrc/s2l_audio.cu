@@ -1,0 +1,145 @@
+// AudioNet + per-frame constants: one CTA per frame, everything in shared memory / registers.
+// Replaces TalkingFace.audio_merge_forward (tf_nerf.py:197-213: 4x Conv1d(k3,s2,p1)+LeakyReLU(0.02),
+// Linear+LeakyReLU+Linear), PositionalEncodingTime (tf_nerf.py:427-442) and the per-frame-constant
+// terms of rgb_forward (fc_audio/fc_time and *_skip, tf_nerf.py:254-258, 270-276).
+// 67 k MAC per frame: far too small for tensor cores; the point is to run it ONCE per frame instead of
+// once per pixel (inference.py:144 tiles the window H*W times) and to emit the layer-0 / skip biases
+// the MLP kernels consume.
+#include "s2l_common.cuh"
+
+namespace s2l {
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.02f * x; }
+
+// out[o][t] = b[o] + sum_c sum_j w[o][c][j] * in[c][2t-1+j], zero padded; in/out in shared memory
+template <int CIN, int COUT, int TIN>
+__device__ __forceinline__ void conv_k3s2(const float* __restrict__ w, const float* __restrict__ b,
+                                          const float* in, float* out, int tid, int nthreads) {
+  constexpr int TOUT = TIN / 2;
+  for (int idx = tid; idx < COUT * TOUT; idx += nthreads) {
+    const int o = idx / TOUT, t = idx % TOUT;
+    float acc = 0.f;
+    const float* wo = w + o * CIN * 3;
+    for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int ti = 2 * t - 1 + j;
+        if (ti >= 0 && ti < TIN) acc = fmaf(wo[c * 3 + j], in[c * TIN + ti], acc);
+      }
+    }
+    out[idx] = lrelu(acc + b[o]);
+  }
+}
+
+__global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __restrict__ blob, Layout L,
+                                                           const float* __restrict__ audio, int transposed,
+                                                           const long long* __restrict__ frame_idx,
+                                                           float* __restrict__ latent, float* __restrict__ frame_bias) {
+  const float* A = reinterpret_cast<const float*>(blob + L.off_audio);
+  const float* C = reinterpret_cast<const float*>(blob + L.off_const);
+  const float* Fp = reinterpret_cast<const float*>(blob + L.off_fp32);
+  __shared__ float x0[kAudioFeat * kAudioWin];   // [29][16]
+  __shared__ float x1[32 * 8], x2[32 * 4], x3[64 * 2], x4[64], x5[64], lat[64];
+  __shared__ float pe[kTimePE];
+  __shared__ float b0s[256], bss[256];
+  const int f = blockIdx.x, tid = threadIdx.x;
+
+  const float* a = audio + (size_t)f * kAudioWin * kAudioFeat;
+  for (int i = tid; i < kAudioFeat * kAudioWin; i += 256) {
+    const int c = i / kAudioWin, t = i % kAudioWin;
+    // tf_nerf.py:203-207: [B,16,29] is permuted to [B,29,16]; a tensor whose last dim is 16 is used as is
+    x0[i] = transposed ? a[c * kAudioWin + t] : a[t * kAudioFeat + c];
+  }
+  if (tid < 10) {
+    float s = 0.f, c = 1.f;
+    if (frame_idx) {
+      const float pos = (float)frame_idx[f];                 // position[0].float(), tf_nerf.py:439
+      const float ang = __fmul_rn(pos, C[C_DIV + tid]);
+      s = sinf(ang);
+      c = cosf(ang);
+    }
+    pe[2 * tid] = s;
+    pe[2 * tid + 1] = c;
+  }
+  __syncthreads();
+  conv_k3s2<29, 32, 16>(A + A_CONV0_W, A + A_CONV0_B, x0, x1, tid, 256);
+  __syncthreads();
+  conv_k3s2<32, 32, 8>(A + A_CONV1_W, A + A_CONV1_B, x1, x2, tid, 256);
+  __syncthreads();
+  conv_k3s2<32, 64, 4>(A + A_CONV2_W, A + A_CONV2_B, x2, x3, tid, 256);
+  __syncthreads();
+  conv_k3s2<64, 64, 2>(A + A_CONV3_W, A + A_CONV3_B, x3, x4, tid, 256);
+  __syncthreads();
+  if (tid < 64) {
+    float acc = 0.f;
+    for (int k = 0; k < 64; ++k) acc = fmaf(A[A_FC1_W + tid * 64 + k], x4[k], acc);
+    x5[tid] = lrelu(acc + A[A_FC1_B + tid]);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float acc = 0.f;
+    for (int k = 0; k < 64; ++k) acc = fmaf(A[A_FC2_W + tid * 64 + k], x5[k], acc);
+    const float v = acc + A[A_FC2_B + tid];
+    lat[tid] = v;
+    if (latent) latent[(size_t)f * kLatent + tid] = v;
+  }
+  __syncthreads();
+  if (!frame_bias) return;
+  {
+    // bias0 = b_uv + (Wa a + b_a) + (Wt t + b_t)   (tf_nerf.py:252-258, same association order)
+    const int n = tid;
+    float ta = 0.f, tas = 0.f, tt = 0.f, tts = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      ta = fmaf(C[C_FCA_WT + k * 256 + n], lat[k], ta);
+      tas = fmaf(C[C_FCAS_WT + k * 256 + n], lat[k], tas);
+    }
+    float b0 = C[C_BIAS6 + 0 * 256 + n] + (ta + C[C_BIAS6 + 1 * 256 + n]);
+    float bs = C[C_BIAS6 + 3 * 256 + n] + (tas + C[C_BIAS6 + 4 * 256 + n]);
+    if (frame_idx) {
+      for (int k = 0; k < kTimePE; ++k) {
+        tt = fmaf(C[C_FCT_WT + k * 256 + n], pe[k], tt);
+        tts = fmaf(C[C_FCTS_WT + k * 256 + n], pe[k], tts);
+      }
+      b0 += (tt + C[C_BIAS6 + 2 * 256 + n]);
+      bs += (tts + C[C_BIAS6 + 5 * 256 + n]);
+    }
+    b0s[n] = b0;
+    bss[n] = bs;
+    float* fb = frame_bias + (size_t)f * 4 * 256;
+    fb[n] = b0;
+    fb[256 + n] = bs;
+  }
+  __syncthreads();
+  {
+    // folded biases for the tensor-core path: W0*bias0 + b0 and W5[:, :256]*bias_skip + b5 (fp64 accumulate)
+    const int n = tid;
+    const float* W0T = Fp + f_pts_off(0);
+    const float* W5T = Fp + f_pts_off(5);
+    double a0 = 0.0, a5 = 0.0;
+    for (int k = 0; k < 256; ++k) {
+      a0 += (double)W0T[k * 256 + n] * (double)b0s[k];
+      a5 += (double)W5T[k * 256 + n] * (double)bss[k];
+    }
+    float* fb = frame_bias + (size_t)f * 4 * 256;
+    fb[512 + n] = (float)(a0 + (double)Fp[F_PTS_B + 0 * 256 + n]);
+    fb[768 + n] = (float)(a5 + (double)Fp[F_PTS_B + 5 * 256 + n]);
+  }
+}
+
+}  // namespace s2l
+
+using namespace s2l;
+
+extern "C" int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, int32_t transposed,
+                                        const int64_t* frame_idx, float* latent, float* frame_bias,
+                                        int32_t n_frames, int32_t uv_dims, int32_t out_ch, void* stream) {
+  (void)uv_dims;
+  (void)out_ch;
+  if (!blob || !audio) { set_error("s2l_audio_encode_fwd: null blob/audio"); return 1; }
+  if (n_frames < 0) { set_error("s2l_audio_encode_fwd: negative n_frames"); return 2; }
+  if (n_frames == 0) return 0;
+  audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed,
+      reinterpret_cast<const long long*>(frame_idx), latent, frame_bias);
+  return check_launch("audio_encode_kernel") ? 0 : 5;
+}

@@ -1,0 +1,170 @@
+// speech2lip_b200 — shared definitions: packed-blob layout, PTX helpers, launch bookkeeping.
+//
+// Data layout in HBM (one blob per model, written by s2l_pack_weights, read-only afterwards,
+// ~6 MB -> L2-resident during a render):
+//   AUDIO   fp32  AudioNet parameters in their PyTorch layouts (tf_nerf.py:91-109)
+//   CONST   fp32  per-frame-constant mat-vec weights (fc_audio/fc_time + *_skip), bias vectors,
+//                 time div_term, folded input weights fold0 = W0*Wuv, fold5 = W5a*Wuv_skip
+//   FP32    fp32  exact-path weights, transposed to [K][256] so a K-chunk is one contiguous 16 KB run
+//   TCBIAS  fp32  per-layer bias rows for the tensor-core path
+//   TCW     bf16  tensor-core B-operand "granules": [64 rows x 64 K] tiles stored as the exact
+//                 shared-memory image the tcgen05 descriptor expects (K-major, 128-byte swizzle),
+//                 hi plane then lo plane (bf16 split of the fp32 weight), in MMA issue order so the
+//                 producer streams them with plain 1-D bulk copies (UBLKCP), no tensor map.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cuda_runtime.h>
+#include "../../include/speech2lip_b200.h"
+
+namespace s2l {
+
+constexpr int kHidden   = 256;
+constexpr int kLatent   = 64;
+constexpr int kTimePE   = 20;
+constexpr int kAudioWin = 16;
+constexpr int kAudioFeat = 29;
+constexpr int kMultires = 10;
+constexpr int kEPad     = 64;      // PE width padded (42 or 63 -> 64)
+constexpr int kNumG     = 9;       // tensor-core GEMM layers after folding (G0..G8)
+constexpr int kOutPad   = 16;      // output layer N padded to the minimum M=128 MMA N
+
+// ---- AUDIO section (float offsets)
+constexpr int A_CONV0_W = 0;
+constexpr int A_CONV0_B = A_CONV0_W + 32 * 29 * 3;
+constexpr int A_CONV1_W = A_CONV0_B + 32;
+constexpr int A_CONV1_B = A_CONV1_W + 32 * 32 * 3;
+constexpr int A_CONV2_W = A_CONV1_B + 32;
+constexpr int A_CONV2_B = A_CONV2_W + 64 * 32 * 3;
+constexpr int A_CONV3_W = A_CONV2_B + 64;
+constexpr int A_CONV3_B = A_CONV3_W + 64 * 64 * 3;
+constexpr int A_FC1_W   = A_CONV3_B + 64;
+constexpr int A_FC1_B   = A_FC1_W + 64 * 64;
+constexpr int A_FC2_W   = A_FC1_B + 64;
+constexpr int A_FC2_B   = A_FC2_W + 64 * 64;
+constexpr int A_TOTAL   = A_FC2_B + 64;          // 32800 floats
+
+// ---- CONST section (float offsets)
+constexpr int C_FCA_WT   = 0;                            // fc_audio^T       [64][256]
+constexpr int C_FCAS_WT  = C_FCA_WT + 64 * 256;          // fc_audio_skip^T  [64][256]
+constexpr int C_FCT_WT   = C_FCAS_WT + 64 * 256;         // fc_time^T        [20][256]
+constexpr int C_FCTS_WT  = C_FCT_WT + 20 * 256;          // fc_time_skip^T   [20][256]
+constexpr int C_BIAS6    = C_FCTS_WT + 20 * 256;         // b_uv,b_a,b_t,b_uvs,b_as,b_ts [6][256]
+constexpr int C_DIV      = C_BIAS6 + 6 * 256;            // div_term[10] (+6 pad)
+constexpr int C_FOLD0    = C_DIV + 16;                   // (W0 * Wuv)        [256][64]  (n-major)
+constexpr int C_FOLD5    = C_FOLD0 + 256 * 64;           // (W5a * Wuv_skip)  [256][64]
+constexpr int C_TOTAL    = C_FOLD5 + 256 * 64;
+
+// ---- FP32 section (float offsets); every matrix is W^T = [K][256]
+constexpr int F_UV_WT    = 0;                            // fc_uv^T       [64][256] (rows >= E are zero)
+constexpr int F_UVS_WT   = F_UV_WT + 64 * 256;           // fc_uv_skip^T  [64][256]
+constexpr int F_PTS_WT   = F_UVS_WT + 64 * 256;          // pts_linears.i^T, i=0..7; .5 has K=512
+__host__ __device__ constexpr int f_pts_off(int i) { return F_PTS_WT + (i <= 5 ? i * 65536 : (i + 1) * 65536); }
+constexpr int F_PTS_B    = F_PTS_WT + 9 * 65536;         // [8][256]
+constexpr int F_OUT_W    = F_PTS_B + 8 * 256;            // output_linear.weight [4][256] (row >= out_ch zero)
+constexpr int F_OUT_B    = F_OUT_W + 4 * 256;            // [4]
+constexpr int F_TOTAL    = F_OUT_B + 4;
+
+// ---- TCW section (byte offsets inside the section)
+constexpr int kGranRows   = 64;                          // N rows per granule (one accumulator quarter)
+constexpr int kGranPlane  = kGranRows * 128;             // 8192 B: [64 rows][64 K] bf16, SW128 K-major
+constexpr int kGranBytes  = 2 * kGranPlane;              // hi + lo
+constexpr int kOutPlane   = kOutPad * 128;               // 2048 B
+constexpr int kOutGranBytes = 2 * kOutPlane;
+__host__ __device__ constexpr int g_nkc(int g) { return g == 0 ? 1 : (g == 5 ? 5 : 4); }
+__host__ __device__ constexpr int g_layer_bytes(int g) { return g == 8 ? 4 * kOutGranBytes : 4 * g_nkc(g) * kGranBytes; }
+__host__ __device__ constexpr int g_layer_off(int g) {
+  int o = 0;
+  for (int i = 0; i < g; ++i) o += g_layer_bytes(i);
+  return o;
+}
+constexpr int kTcwBytes = g_layer_off(kNumG);            // 1 982 464 B per tile pass
+constexpr int kGranPerTile = 4 * (1 + 4 * 4 + 5 + 2 * 4) + 4;   // 124
+
+struct Layout {
+  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, total;
+};
+__host__ __device__ inline Layout blob_layout() {
+  Layout L;
+  size_t o = 0;
+  auto al = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+  L.off_audio = o;  o = al(o + sizeof(float) * A_TOTAL);
+  L.off_const = o;  o = al(o + sizeof(float) * C_TOTAL);
+  L.off_fp32 = o;   o = al(o + sizeof(float) * F_TOTAL);
+  L.off_tcbias = o; o = al(o + sizeof(float) * kNumG * 256);
+  L.off_tcw = o;    o = al(o + kTcwBytes);
+  L.total = o;
+  return L;
+}
+
+__host__ __device__ inline int pe_dim(int uv_dims) { return uv_dims + 2 * kMultires * uv_dims; }
+
+// byte offset of element (row n, k) inside a K-major 128B-swizzled [rows][64] bf16 tile
+__host__ __device__ inline int sw128_off(int n, int k) {
+  return (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2;
+}
+
+// ------------------------------------------------------------------ error / launch bookkeeping (host)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+bool check_launch(const char* what);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// torch.linspace(0,1,n)[i] as ATen computes it on CUDA and CPU (symmetric halves, fp32 step):
+//   step = (end-start)/(n-1);  i < n/2 ? start + i*step : end - (n-1-i)*step
+__device__ __forceinline__ float linspace01(int i, int n) {
+  if (n == 1) return 0.f;
+  const float step = __fdiv_rn(1.0f, (float)(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(n - 1 - i)));
+}
+#endif  // __CUDACC__
+
+}  // namespace s2l

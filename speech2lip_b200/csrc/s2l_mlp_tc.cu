@@ -1,0 +1,455 @@
+// Throughput path: the fused per-point MLP on 5th-gen tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// One persistent CTA per SM walks 128-point tiles.  Per tile it evaluates the folded layer program
+//   G0  relu(fold0 * PE + bias0'[f])                 K = 64          (fc_uv folded into pts_linears.0)
+//   G1-4 relu(W_g h + b_g)                            K = 256
+//   G5  relu(fold5 * PE + W5b h + bias5'[f])          K = 64 + 256    (fc_uv_skip folded into pts_linears.5)
+//   G6-7 relu(W_g h + b_g)                            K = 256
+//   G8  W_out h + b_out                               K = 256, N = 16 (out_ch padded)
+// which is algebraically TalkingFace.rgb_forward (tf_nerf.py:225-285) with the per-frame-constant
+// audio/time terms hoisted into bias0'/bias5' (s2l_audio.cu).
+//
+// Where the data lives
+//   activations : TMEM only.  The 512 columns are two 256-column regions R0/R1 that swap roles every
+//                 layer: tcgen05.mma accumulates D_g (fp32, 128 lanes x 256 cols) into one region while
+//                 reading A_g (bf16 hi/lo, packed 2 per column) from the other.  The epilogue converts
+//                 D_g -> A_{g+1} IN PLACE, one 64-column quarter at a time (tcgen05.ld -> +bias, ReLU,
+//                 bf16 hi/lo split -> tcgen05.st over the same columns), so the next layer's MMAs over
+//                 K-chunk q start as soon as quarter q is converted while later quarters still compute.
+//   weights     : streamed from L2 (blob TCW section, pre-swizzled smem images) by 1-D bulk copies
+//                 into a 9-stage ring of 16 KB granules (64 N-rows x 64 K, hi plane + lo plane).
+//   PE          : computed by 4 dedicated warps one tile ahead, written as a K-major SW128 bf16 hi/lo
+//                 A-operand image in shared memory (used by G0 and again by G5).
+//
+// Precision: NPASS = 3 issues hi*hi + lo*hi + hi*lo (bf16 split, fp32 accumulate) ~ 2^-17 relative
+// per product — this is the parity mode (<= 1e-3 max-abs).  NPASS = 1 issues hi*hi only.
+//
+// Warp roles (512 threads): w0 weight producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
+// w4-7 PE producers, w8-15 epilogue (two warps per TMEM lane quadrant, 32 columns each).
+#include <cuda_bf16.h>
+#include <cstdio>
+#include "s2l_common.cuh"
+#include "s2l_points.cuh"
+
+namespace s2l {
+
+constexpr int TC_TM = 128;
+constexpr int TC_THREADS = 512;
+constexpr int NSTG = 9;
+constexpr int PE_PLANE = TC_TM * 128;              // 16 KB: [128 rows][64 K] bf16, SW128
+constexpr int PE_BUF = 2 * PE_PLANE;               // hi + lo
+constexpr int SM_PE = 0;                           // 2 buffers
+constexpr int SM_STG = SM_PE + 2 * PE_BUF;         // 65536
+constexpr int SM_TCBIAS = SM_STG + NSTG * kGranBytes;
+constexpr int SM_FBIAS = SM_TCBIAS + kNumG * 256 * 4;
+constexpr int SM_BAR = SM_FBIAS + 2 * 2 * 256 * 4;
+constexpr int NBAR = 2 * NSTG + 2 + 2 + 4 + 4;
+constexpr int SM_TMEMPTR = SM_BAR + NBAR * 8;
+constexpr int TC_SMEM_BYTES = SM_TMEMPTR + 16;
+
+struct TcArgs {
+  const uint8_t* blob;
+  Layout L;
+  PointSrc src;
+  const float* frame_bias;   // [F,4,256]; rows 2,3 = folded bias0', bias5'
+  float* out;                // [F*P, out_ch]
+  int out_ch;
+  int n_frames;
+  long long tiles_per_frame;
+};
+
+// ------------------------------------------------------------------ tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (8-row atoms of 1024 B):
+// start>>4 | LBO=1 (unused for swizzled K-major) | SBO=1024>>4 | version=1 (sm_100) | layout=SWIZZLE_128B
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// Bounded mbarrier wait: a protocol bug must surface as a trapped kernel, never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("s2l tc kernel: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);     // .x (low 16 bits) = lo, .y = hi
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int NPASS, int UVD>
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + NSTG;
+  uint64_t* pe_full = bars + 2 * NSTG;
+  uint64_t* pe_empty = pe_full + 2;
+  uint64_t* acc_full = pe_empty + 2;
+  uint64_t* epi_done = acc_full + 4;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
+  float* tcbias_s = reinterpret_cast<float*>(smem + SM_TCBIAS);
+  float* fbias_s = reinterpret_cast<float*>(smem + SM_FBIAS);   // [2 bufs][2][256]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_tiles = a.tiles_per_frame * a.n_frames;
+  const uint8_t* tcw = a.blob + a.L.off_tcw;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&pe_full[b], 128);
+      mbar_init(&pe_empty[b], 1 + 256);
+    }
+    for (int q = 0; q < 4; ++q) {
+      mbar_init(&acc_full[q], 1);
+      mbar_init(&epi_done[q], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const float* TB = reinterpret_cast<const float*>(a.blob + a.L.off_tcbias);
+    for (int i = tid; i < kNumG * 256; i += TC_THREADS) tcbias_s[i] = TB[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // =============================================================== weight producer
+    if (elect_one()) {
+      long long c = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int g = 0; g < kNumG; ++g) {
+          const int ngran = (g == 8) ? 4 : 4 * g_nkc(g);
+          const int plane = (g == 8) ? kOutPlane : kGranPlane;
+          const uint8_t* src = tcw + g_layer_off(g);
+          for (int gi = 0; gi < ngran; ++gi, ++c) {
+            const int stage = (int)(c % NSTG);
+            mbar_wait_wd(&b_empty[stage], (uint32_t)(((c / NSTG) & 1) ^ 1), 100 + stage);
+            uint8_t* dst = smem + SM_STG + stage * kGranBytes;
+            if (NPASS == 3) {
+              mbar_arrive_expect_tx(&b_full[stage], 2 * plane);
+              bulk_g2s(dst, src + (size_t)gi * 2 * plane, 2 * plane, &b_full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&b_full[stage], plane);
+              bulk_g2s(dst, src + (size_t)gi * 2 * plane, plane, &b_full[stage]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (one thread)
+    if (elect_one()) {
+      long long c = 0;
+      uint32_t epi_par[4] = {0, 0, 0, 0};
+      int rp = 0;
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        const uint32_t pe_hi = smem_u32(smem + SM_PE + buf * PE_BUF);
+        const uint32_t pe_lo = pe_hi + PE_PLANE;
+        for (int g = 0; g < kNumG; ++g) {
+          const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
+          const uint32_t a_region = tmem_base + (rp ? 0u : 256u);
+          const int nq = (g == 8) ? 1 : 4;
+          const uint32_t idesc = (g == 8) ? idesc_bf16(kOutPad) : idesc_bf16(64);
+          const int plane = (g == 8) ? kOutPlane : kGranPlane;
+          const int nkc = g_nkc(g);
+          for (int q = 0; q < nq; ++q) {
+            const uint32_t d_addr = d_region + (uint32_t)q * 64u;
+            for (int kc = 0; kc < nkc; ++kc, ++c) {
+              const bool is_pe = (g == 0) || (g == 5 && kc == 0);
+              const int hk = (g == 5) ? kc - 1 : kc;
+              if (q == 0) {
+                if (g == 0) mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 200 + buf);
+                if (!is_pe) {
+                  mbar_wait_wd(&epi_done[hk], epi_par[hk], 300 + hk);
+                  epi_par[hk] ^= 1;
+                }
+              }
+              const int stage = (int)(c % NSTG);
+              mbar_wait_wd(&b_full[stage], (uint32_t)((c / NSTG) & 1), 400 + stage);
+              tc_fence_after();
+              const uint32_t b_hi = smem_u32(smem + SM_STG + stage * kGranBytes);
+              const uint32_t b_lo = b_hi + plane;
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const uint32_t acc0 = (kc == 0 && s == 0) ? 0u : 1u;
+                const uint64_t bd_hi = sw128_desc(b_hi + s * 32);
+                if (is_pe) {
+                  const uint64_t ad_hi = sw128_desc(pe_hi + s * 32);
+                  umma_ss(d_addr, ad_hi, bd_hi, idesc, acc0);
+                  if (NPASS == 3) {
+                    umma_ss(d_addr, sw128_desc(pe_lo + s * 32), bd_hi, idesc, 1u);
+                    umma_ss(d_addr, ad_hi, sw128_desc(b_lo + s * 32), idesc, 1u);
+                  }
+                } else {
+                  // A chunk layout in TMEM (64 cols): [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
+                  const uint32_t a_hi = a_region + (uint32_t)hk * 64u + (uint32_t)(s >> 1) * 32u + (uint32_t)(s & 1) * 8u;
+                  umma_ts(d_addr, a_hi, bd_hi, idesc, acc0);
+                  if (NPASS == 3) {
+                    umma_ts(d_addr, a_hi + 16u, bd_hi, idesc, 1u);
+                    umma_ts(d_addr, a_hi, sw128_desc(b_lo + s * 32), idesc, 1u);
+                  }
+                }
+              }
+              umma_commit(&b_empty[stage]);      // stage reusable once these MMAs retire
+            }
+            umma_commit(&acc_full[q]);           // accumulator quarter q of layer g complete
+          }
+          if (g == 5) umma_commit(&pe_empty[buf]);   // last reader of this tile's PE image
+          rp ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =============================================================== PE producers (one point per thread)
+    const int r = tid - 128;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      const int f = (int)(tile / a.tiles_per_frame);
+      const long long p = (tile % a.tiles_per_frame) * TC_TM + r;
+      mbar_wait_wd(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
+      float e[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) e[i] = 0.f;
+      if (p < a.src.P) {
+        float x[3];
+        gen_point(a.src, f, p, x);
+#pragma unroll
+        for (int d = 0; d < UVD; ++d) e[d] = x[d];
+#pragma unroll
+        for (int k = 0; k < kMultires; ++k) {
+#pragma unroll
+          for (int d = 0; d < UVD; ++d) {
+            float sn, cs;
+            sincosf(__fmul_rn(x[d], (float)(1 << k)), &sn, &cs);     // tf_nerf.py:412: p_fn(x * freq)
+            e[UVD + (2 * k) * UVD + d] = sn;
+            e[UVD + (2 * k + 1) * UVD + d] = cs;
+          }
+        }
+      }
+      uint8_t* hi_base = smem + SM_PE + buf * PE_BUF;
+      uint8_t* lo_base = hi_base + PE_PLANE;
+      const int row_off = (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float v0 = e[8 * j + 2 * t], v1 = e[8 * j + 2 * t + 1];
+          const uint32_t hp = pack_bf16x2(v0, v1);
+          h[t] = hp;
+          l[t] = pack_bf16x2(v0 - __uint_as_float(hp << 16), v1 - __uint_as_float(hp & 0xffff0000u));
+        }
+        const int off = row_off + ((j ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (NPASS == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      {
+        const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
+        float* dst = fbias_s + buf * 512;
+        for (int i = r; i < 512; i += 128) dst[i] = fb[i];
+      }
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core's async proxy
+      mbar_arrive(&pe_full[buf]);
+    }
+  } else if (warp >= 8) {
+    // =============================================================== epilogue
+    const int quad = warp & 3, half = (warp - 8) >> 2;
+    const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+    const int row = quad * 32 + lane;
+    uint32_t acc_par[4] = {0, 0, 0, 0};
+    int rp = 0;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      const int f = (int)(tile / a.tiles_per_frame);
+      const long long p = (tile % a.tiles_per_frame) * TC_TM + row;
+      mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 600 + buf);   // folded per-frame biases staged
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
+        const float* bias = (g == 0) ? (fbias_s + buf * 512) : (g == 5) ? (fbias_s + buf * 512 + 256) : (tcbias_s + g * 256);
+        for (int q = 0; q < 4; ++q) {
+          mbar_wait_wd(&acc_full[q], acc_par[q], 700 + q);
+          acc_par[q] ^= 1;
+          tc_fence_after();
+          const uint32_t taddr = d_region + lane_sel + (uint32_t)(q * 64 + half * 32);
+          uint32_t v[32];
+          tmem_ld32(taddr, v);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + half * 32);
+          uint32_t o[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bb = b4[j4];
+            const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
+            const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+            const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
+            const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+            const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
+            o[2 * j4] = h0;
+            o[2 * j4 + 1] = h1;
+            if (NPASS == 3) {
+              o[16 + 2 * j4] = pack_bf16x2(x0 - __uint_as_float(h0 << 16), x1 - __uint_as_float(h0 & 0xffff0000u));
+              o[16 + 2 * j4 + 1] = pack_bf16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u));
+            }
+          }
+          if (NPASS == 3) tmem_st32(taddr, o);
+          else tmem_st16(taddr, o);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&epi_done[q]);
+        }
+        if (g == 5) mbar_arrive(&pe_empty[buf]);      // this thread no longer reads fbias_s[buf]
+        rp ^= 1;
+      }
+      // ---- G8: raw output (no activation), tf_nerf.py:283
+      {
+        const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
+        mbar_wait_wd(&acc_full[0], acc_par[0], 800);
+        acc_par[0] ^= 1;
+        tc_fence_after();
+        if (half == 0) {
+          uint32_t v[4];
+          tmem_ld4(d_region + lane_sel, v);
+          tmem_ld_wait();
+          if (p < a.src.P) {
+            float* o = a.out + ((long long)f * a.src.P + p) * a.out_ch;
+            const float* bo = tcbias_s + 8 * 256;
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+              if (n < a.out_ch) o[n] = __uint_as_float(v[n]) + bo[n];
+          }
+        }
+        rp ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+template <int NPASS, int UVD>
+static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+      set_error("mlp_tc: cannot opt in to %d B of shared memory: %s", TC_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
+      return 6;
+    }
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+  mlp_tc_kernel<NPASS, UVD><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+  return check_launch("mlp_tc_kernel") ? 0 : 5;
+}
+
+int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
+                  int npass, cudaStream_t st) {
+  TcArgs a{};
+  a.blob = reinterpret_cast<const uint8_t*>(blob);
+  a.L = blob_layout();
+  a.src = src;
+  a.frame_bias = frame_bias;
+  a.out = out;
+  a.out_ch = out_ch;
+  a.n_frames = n_frames;
+  a.tiles_per_frame = (src.P + TC_TM - 1) / TC_TM;
+  const long long n_tiles = a.tiles_per_frame * n_frames;
+  if (n_tiles == 0) return 0;
+  if (src.uv_dims == 2) return npass == 3 ? launch_tc_impl<3, 2>(a, n_tiles, st) : launch_tc_impl<1, 2>(a, n_tiles, st);
+  if (src.uv_dims == 3) return npass == 3 ? launch_tc_impl<3, 3>(a, n_tiles, st) : launch_tc_impl<1, 3>(a, n_tiles, st);
+  set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims);
+  return 2;
+}
+
+}  // namespace s2l

@@ -1,0 +1,193 @@
+// s2l_pack_weights: PyTorch-layout fp32 parameters -> kernel-layout blob (see s2l_common.cuh).
+// Replaces the parameter inventory of TalkingFace.__init__ (tf_nerf.py:85-172) on the device side.
+#include <cmath>
+#include <cuda_bf16.h>
+#include "s2l_common.cuh"
+
+namespace s2l {
+
+struct ParamPtrs {
+  const float* p[S2L_NUM_PARAMS];
+};
+struct DivTerm {
+  float v[16];
+};
+
+__device__ __forceinline__ const float* pts_w(const ParamPtrs& P, int i) { return P.p[S2L_P_PTS0_W + 2 * i]; }
+__device__ __forceinline__ const float* pts_b(const ParamPtrs& P, int i) { return P.p[S2L_P_PTS0_W + 2 * i + 1]; }
+
+// ---- AUDIO + CONST (except folds) + FP32 + TCBIAS: pure re-layout, one grid-stride pass per section
+__global__ void pack_relayout_kernel(ParamPtrs P, uint8_t* blob, Layout L, int E, int out_ch, DivTerm div_term) {
+  float* A = reinterpret_cast<float*>(blob + L.off_audio);
+  float* C = reinterpret_cast<float*>(blob + L.off_const);
+  float* Fp = reinterpret_cast<float*>(blob + L.off_fp32);
+  float* TB = reinterpret_cast<float*>(blob + L.off_tcbias);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+
+  // AUDIO: straight copies
+  const int a_off[13] = {A_CONV0_W, A_CONV0_B, A_CONV1_W, A_CONV1_B, A_CONV2_W, A_CONV2_B, A_CONV3_W,
+                         A_CONV3_B, A_FC1_W,   A_FC1_B,   A_FC2_W,   A_FC2_B,   A_TOTAL};
+  for (int t = 0; t < 12; ++t) {
+    const float* src = P.p[S2L_P_CONV0_W + t];
+    const int n = a_off[t + 1] - a_off[t];
+    for (int i = tid; i < n; i += nth) A[a_off[t] + i] = src[i];
+  }
+  // CONST: transposed per-frame mat-vec weights
+  for (int i = tid; i < 64 * 256; i += nth) {
+    const int k = i / 256, n = i % 256;
+    C[C_FCA_WT + i] = P.p[S2L_P_FC_AUDIO_W][n * 64 + k];
+    C[C_FCAS_WT + i] = P.p[S2L_P_FC_AUDIO_SKIP_W][n * 64 + k];
+  }
+  for (int i = tid; i < 20 * 256; i += nth) {
+    const int k = i / 256, n = i % 256;
+    C[C_FCT_WT + i] = P.p[S2L_P_FC_TIME_W][n * 20 + k];
+    C[C_FCTS_WT + i] = P.p[S2L_P_FC_TIME_SKIP_W][n * 20 + k];
+  }
+  for (int i = tid; i < 256; i += nth) {
+    C[C_BIAS6 + 0 * 256 + i] = P.p[S2L_P_FC_UV_B][i];
+    C[C_BIAS6 + 1 * 256 + i] = P.p[S2L_P_FC_AUDIO_B][i];
+    C[C_BIAS6 + 2 * 256 + i] = P.p[S2L_P_FC_TIME_B][i];
+    C[C_BIAS6 + 3 * 256 + i] = P.p[S2L_P_FC_UV_SKIP_B][i];
+    C[C_BIAS6 + 4 * 256 + i] = P.p[S2L_P_FC_AUDIO_SKIP_B][i];
+    C[C_BIAS6 + 5 * 256 + i] = P.p[S2L_P_FC_TIME_SKIP_B][i];
+  }
+  for (int i = tid; i < 16; i += nth) C[C_DIV + i] = (i < 10) ? div_term.v[i] : 0.f;
+
+  // FP32: W^T [K][256]
+  for (int i = tid; i < 64 * 256; i += nth) {
+    const int k = i / 256, n = i % 256;
+    Fp[F_UV_WT + i] = (k < E) ? P.p[S2L_P_FC_UV_W][n * E + k] : 0.f;
+    Fp[F_UVS_WT + i] = (k < E) ? P.p[S2L_P_FC_UV_SKIP_W][n * E + k] : 0.f;
+  }
+  for (int l = 0; l < 8; ++l) {
+    const int K = (l == 5) ? 512 : 256;
+    const float* w = pts_w(P, l);
+    float* dst = Fp + f_pts_off(l);
+    for (int i = tid; i < K * 256; i += nth) {
+      const int k = i / 256, n = i % 256;
+      dst[i] = w[n * K + k];
+    }
+    for (int i = tid; i < 256; i += nth) Fp[F_PTS_B + l * 256 + i] = pts_b(P, l)[i];
+  }
+  for (int i = tid; i < 4 * 256; i += nth) {
+    const int n = i / 256, k = i % 256;
+    Fp[F_OUT_W + i] = (n < out_ch) ? P.p[S2L_P_OUT_W][n * 256 + k] : 0.f;
+  }
+  for (int i = tid; i < 4; i += nth) Fp[F_OUT_B + i] = (i < out_ch) ? P.p[S2L_P_OUT_B][i] : 0.f;
+
+  // TCBIAS [9][256]: G0/G5 rows unused (per-frame folded bias), G8 = output bias padded
+  for (int i = tid; i < kNumG * 256; i += nth) {
+    const int g = i / 256, n = i % 256;
+    float v = 0.f;
+    if (g >= 1 && g <= 7 && g != 5) v = pts_b(P, g)[n];
+    if (g == 8 && n < out_ch) v = P.p[S2L_P_OUT_B][n];
+    TB[i] = v;
+  }
+}
+
+// ---- folded input weights (two back-to-back Linear layers without a nonlinearity between them,
+//      tf_nerf.py:252-266 and :268-281):  fold0 = W0 * Wuv,  fold5 = W5[:, :256] * Wuv_skip.  fp64 accumulate.
+__global__ void pack_fold_kernel(ParamPtrs P, uint8_t* blob, Layout L, int E) {
+  float* C = reinterpret_cast<float*>(blob + L.off_const);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // 2 * 256 * 64
+  if (idx >= 2 * 256 * 64) return;
+  const int which = idx / (256 * 64);
+  const int n = (idx / 64) % 256, e = idx % 64;
+  double acc = 0.0;
+  if (e < E) {
+    const float* Wl = which == 0 ? pts_w(P, 0) : pts_w(P, 5);
+    const int ldl = which == 0 ? 256 : 512;
+    const float* Wi = which == 0 ? P.p[S2L_P_FC_UV_W] : P.p[S2L_P_FC_UV_SKIP_W];
+    for (int k = 0; k < 256; ++k) acc += (double)Wl[n * ldl + k] * (double)Wi[k * E + e];
+  }
+  C[(which == 0 ? C_FOLD0 : C_FOLD5) + n * 64 + e] = (float)acc;
+}
+
+// ---- tensor-core operand granules: hi/lo bf16 split, K-major SW128 smem image, MMA issue order
+__global__ void pack_tcw_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch) {
+  const float* C = reinterpret_cast<const float*>(blob + L.off_const);
+  uint8_t* T = blob + L.off_tcw;
+  // one thread per (granule, row, k) element; granule index space = sum over layers
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // decode: layers 0..7 have 4*nkc granules of 64x64; layer 8 has 4 granules of 16x64
+  long long rem = gid;
+  int g = 0, rows = 64;
+  for (; g < kNumG; ++g) {
+    rows = (g == 8) ? kOutPad : 64;
+    const long long cnt = (long long)((g == 8) ? 4 : 4 * g_nkc(g)) * rows * 64;
+    if (rem < cnt) break;
+    rem -= cnt;
+  }
+  if (g >= kNumG) return;
+  const int per_gran = rows * 64;
+  const int gi = (int)(rem / per_gran);
+  const int r = (int)(rem % per_gran);
+  const int n = r / 64, k = r % 64;
+  const int nkc = g_nkc(g);
+  const int q = (g == 8) ? 0 : gi / nkc;
+  const int kc = (g == 8) ? gi : gi % nkc;
+  const int ng = q * 64 + n;
+  float v;
+  if (g == 0) {
+    v = C[C_FOLD0 + ng * 64 + k];
+  } else if (g == 5) {
+    v = (kc == 0) ? C[C_FOLD5 + ng * 64 + k] : pts_w(P, 5)[ng * 512 + 256 + (kc - 1) * 64 + k];
+  } else if (g == 8) {
+    v = (n < out_ch) ? P.p[S2L_P_OUT_W][n * 256 + kc * 64 + k] : 0.f;
+  } else {
+    v = pts_w(P, g)[ng * 256 + kc * 64 + k];
+  }
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const int plane = (g == 8) ? kOutPlane : kGranPlane;
+  uint8_t* base = T + g_layer_off(g) + (size_t)gi * (2 * plane);
+  const int off = sw128_off(n, k);
+  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(base + plane + off) = lo;
+}
+
+}  // namespace s2l
+
+using namespace s2l;
+
+// PositionalEncodingTime.div_term (tf_nerf.py:431-432): exp(arange(0,20,2) * -(ln(1e4)/20)) in fp32.
+extern "C" void s2l_time_div_term(float* out10) {
+  const float c = (float)(-(std::log(10000.0) / 20.0));
+  for (int i = 0; i < 10; ++i) out10[i] = std::exp((float)(2 * i) * c);
+}
+
+extern "C" size_t s2l_blob_bytes(int32_t uv_dims, int32_t out_ch) {
+  (void)uv_dims;
+  (void)out_ch;
+  return blob_layout().total;
+}
+
+extern "C" int32_t s2l_pack_weights(const float* const* params_host, void* blob, int32_t uv_dims, int32_t out_ch,
+                                    void* stream) {
+  if (!params_host || !blob) { set_error("s2l_pack_weights: null argument"); return 1; }
+  if ((uv_dims != 2 && uv_dims != 3) || out_ch < 1 || out_ch > 4) {
+    set_error("s2l_pack_weights: unsupported dims uv_dims=%d out_ch=%d (need uv_dims in {2,3}, out_ch in 1..4)", uv_dims, out_ch);
+    return 2;
+  }
+  ParamPtrs P;
+  for (int i = 0; i < S2L_NUM_PARAMS; ++i) {
+    if (!params_host[i]) { set_error("s2l_pack_weights: parameter %d is null", i); return 3; }
+    P.p[i] = params_host[i];
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Layout L = blob_layout();
+  const int E = pe_dim(uv_dims);
+  DivTerm dt;
+  s2l_time_div_term(dt.v);
+  for (int i = 10; i < 16; ++i) dt.v[i] = 0.f;
+  uint8_t* b = reinterpret_cast<uint8_t*>(blob);
+  pack_relayout_kernel<<<148, 256, 0, st>>>(P, b, L, E, out_ch, dt);
+  if (!check_launch("pack_relayout_kernel")) return 5;
+  pack_fold_kernel<<<(2 * 256 * 64 + 255) / 256, 256, 0, st>>>(P, b, L, E);
+  if (!check_launch("pack_fold_kernel")) return 5;
+  const long long n_elem = (long long)kTcwBytes / 4;   // one thread per (hi,lo) element pair
+  pack_tcw_kernel<<<(unsigned)((n_elem + 255) / 256), 256, 0, st>>>(P, b, L, out_ch);
+  if (!check_launch("pack_tcw_kernel")) return 5;
+  return 0;
+}

@@ -1,0 +1,159 @@
+// Per-pixel reductions after the MLP and ray generation:
+//   ensemble4_blend_kernel — 4-tap area-weighted blend of Trainer.predict_lip_image (training.py:237-249)
+//   composite_kernel       — density2outputs (rendering.py:30-62): one warp per ray, shuffle scan over samples
+//   get_rays_kernel        — get_rays (src/common.py:12-21)
+// All three are HBM-bound streaming kernels (16 B read per point); coalesced float4 loads, no staging needed.
+#include "s2l_common.cuh"
+#include "s2l_points.cuh"
+
+namespace s2l {
+
+__global__ void ensemble4_blend_kernel(const float* __restrict__ raw, PointSrc src, int n_frames, int out_ch,
+                                       float* __restrict__ rgb) {
+  const long long npix = (long long)src.H * src.W;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= npix * n_frames) return;
+  const int f = (int)(gid / npix);
+  const long long pix = gid % npix;
+  const int px = (int)(pix % src.W), py = (int)(pix / src.W);
+  const float u0 = linspace01(px, src.W), v0 = linspace01(py, src.H);
+  float area[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float x[3];
+    gen_point(src, f, pix * 4 + t, x);
+    area[t] = ens4_area(x[0], x[1], u0, v0);
+  }
+  // tot_area = stack(areas).sum(0); then areas 0<->3, 1<->2 are swapped (training.py:243-245)
+  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+  const float* r = raw + (gid * 4) * out_ch;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float w = __fdiv_rn(area[3 - t], tot);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c < out_ch) acc[c] = __fadd_rn(acc[c], __fmul_rn(r[t * out_ch + c], w));
+  }
+  for (int c = 0; c < 3; ++c) rgb[gid * 3 + c] = acc[c];
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+
+// One warp per ray.  weights_i = alpha_i * prod_{j<i} (1 - alpha_j + 1e-10); rgb = sum w*sigmoid(c); depth = sum w*z.
+__global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
+                                                        int z_per_ray, const float* __restrict__ rays_d,
+                                                        long long n_rays, long long rays_mod, int S,
+                                                        float* __restrict__ rgb, float* __restrict__ weights,
+                                                        float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31;
+  const long long ray = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= n_rays) return;
+  const long long dr = rays_mod > 0 ? ray % rays_mod : ray;
+  const float dx = rays_d[dr * 3 + 0], dy = rays_d[dr * 3 + 1], dz = rays_d[dr * 3 + 2];
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const float* zr = z_per_ray ? z_vals + ray * S : z_vals;
+  const float4* rr = reinterpret_cast<const float4*>(raw) + ray * S;
+  float carry = 1.f, ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < S;
+    float alpha = 0.f, zi = 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      v = __ldg(rr + i);
+      zi = zr[i];
+      const float dist = __fmul_rn((i + 1 < S) ? __fsub_rn(zr[i + 1], zi) : 1e10f, nrm);
+      alpha = __fsub_rn(1.f, expf(-__fmul_rn(fmaxf(v.w, 0.f), dist)));
+    }
+    const float t = valid ? __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f) : 1.f;
+    float incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= up;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    const float w = alpha * (carry * excl);
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    if (valid) {
+      if (weights) weights[ray * S + i] = w;
+      ar = fmaf(w, sigmoidf_acc(v.x), ar);
+      ag = fmaf(w, sigmoidf_acc(v.y), ag);
+      ab = fmaf(w, sigmoidf_acc(v.z), ab);
+      ad = fmaf(w, zi, ad);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ag += __shfl_xor_sync(0xffffffffu, ag, o);
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    ad += __shfl_xor_sync(0xffffffffu, ad, o);
+  }
+  if (lane == 0) {
+    rgb[ray * 3 + 0] = ar;
+    rgb[ray * 3 + 1] = ag;
+    rgb[ray * 3 + 2] = ab;
+    if (depth) depth[ray] = ad;
+  }
+}
+
+__global__ void get_rays_kernel(const float* __restrict__ c2w, int H, int W, float focal, float* __restrict__ rays_o,
+                                float* __restrict__ rays_d) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= H * W) return;
+  const float i = (float)(gid % W), j = (float)(gid / W);
+  const float d0 = __fdiv_rn(__fsub_rn(i, (float)(W * 0.5)), focal);
+  const float d1 = __fdiv_rn(-__fsub_rn(j, (float)(H * 0.5)), focal);
+  const float d2 = -1.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(d0, c2w[c * 4 + 0]), __fmul_rn(d1, c2w[c * 4 + 1])), __fmul_rn(d2, c2w[c * 4 + 2]));
+    rays_d[gid * 3 + c] = s;
+    rays_o[gid * 3 + c] = c2w[c * 4 + 3];
+  }
+}
+
+}  // namespace s2l
+
+using namespace s2l;
+
+extern "C" int32_t s2l_ensemble4_blend(const float* raw, const S2LGeom* g, float* rgb, void* stream) {
+  if (!raw || !g || !rgb) { set_error("s2l_ensemble4_blend: null argument"); return 1; }
+  PointSrc src{};
+  src.mode = S2L_PTS_GRID_ENS4;
+  src.H = g->height;
+  src.W = g->width;
+  src.uv_dims = 2;
+  src.eps = g->eps_shift;
+  src.P = (long long)g->height * g->width * 4;
+  const long long n = (long long)g->height * g->width * g->n_frames;
+  if (n == 0) return 0;
+  ensemble4_blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      raw, src, g->n_frames, g->out_ch, rgb);
+  return check_launch("ensemble4_blend_kernel") ? 0 : 5;
+}
+
+extern "C" int32_t s2l_composite_fwd(const float* raw, const float* z_vals, int32_t z_per_ray, const float* rays_d,
+                                     int64_t n_rays, int64_t rays_mod, int32_t n_samples, float* rgb, float* weights,
+                                     float* depth, void* stream) {
+  if (!raw || !z_vals || !rays_d || !rgb) { set_error("s2l_composite_fwd: null argument"); return 1; }
+  if (n_samples < 1) { set_error("s2l_composite_fwd: n_samples must be >= 1 (got %d)", n_samples); return 2; }
+  if (n_rays == 0) return 0;
+  const long long threads = (long long)n_rays * 32;
+  composite_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      raw, z_vals, z_per_ray, rays_d, n_rays, rays_mod, n_samples, rgb, weights, depth);
+  return check_launch("composite_kernel") ? 0 : 5;
+}
+
+extern "C" int32_t s2l_get_rays(const float* c2w, int32_t height, int32_t width, float focal, float* rays_o,
+                                float* rays_d, void* stream) {
+  if (!c2w || !rays_o || !rays_d) { set_error("s2l_get_rays: null argument"); return 1; }
+  const int n = height * width;
+  if (n == 0) return 0;
+  get_rays_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c2w, height, width, focal,
+                                                                                        rays_o, rays_d);
+  return check_launch("get_rays_kernel") ? 0 : 5;
+}

@@ -1,0 +1,263 @@
+"""Host side of the hot path: packed weights + the batched frame renderer.
+
+Everything here is plumbing around the C ABI (include/speech2lip_b200.h): torch owns device memory
+and streams, the CUDA library does the arithmetic.  There is no PyTorch implementation of the path in
+this package — if the CUDA library is missing or the tensors are not on a CUDA device, calls raise.
+
+Reference call sites this replaces:
+  inference.py:144-159                     -> LipRenderer.render_frames(mode="plain")
+  src/face_simple/training.py:158-251      -> LipRenderer.render_frames(mode="ensemble4")
+  TalkingFace(uv_dims=3,output_ch=4) + src/common.py:12-21 + src/face_simple/rendering.py:30-62
+                                           -> LipRenderer.render_frames(mode="volumetric")
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import S2LGeom
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("speech2lip_b200: %s must be a CUDA tensor (the hot path has no CPU fallback)" % name)
+
+
+def _f32c(t, name):
+    _need_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class PackedWeights:
+    """Kernel-layout copy of the hot-path parameters (s2l_pack_weights).  `params` maps the reference's
+    state_dict names (tf_nerf.py:85-172) to CUDA fp32 tensors; call repack() after they change."""
+
+    def __init__(self, params, uv_dims=2, out_ch=3):
+        self.uv_dims = int(uv_dims)
+        self.out_ch = int(out_ch)
+        self.blob = None
+        self.repack(params)
+
+    def repack(self, params):
+        lib = _cabi.lib()
+        tensors = []
+        for name in _cabi.PARAM_NAMES:
+            if name not in params:
+                raise KeyError("speech2lip_b200: parameter %r missing from the state dict" % name)
+            t = params[name]
+            t = t.detach() if isinstance(t, torch.Tensor) else torch.as_tensor(t)
+            tensors.append(_f32c(t, name))
+        e = self.uv_dims + 20 * self.uv_dims
+        if tuple(tensors[_cabi.PARAM_NAMES.index("fc_uv.weight")].shape) != (256, e):
+            raise ValueError("fc_uv.weight has shape %s, expected (256, %d) for uv_dims=%d"
+                             % (tuple(params["fc_uv.weight"].shape), e, self.uv_dims))
+        if tensors[_cabi.PARAM_NAMES.index("output_linear.weight")].shape[0] != self.out_ch:
+            raise ValueError("output_linear.weight rows != out_ch=%d" % self.out_ch)
+        dev = tensors[0].device
+        if self.blob is None or self.blob.device != dev:
+            self.blob = torch.empty(lib.s2l_blob_bytes(self.uv_dims, self.out_ch), dtype=torch.uint8, device=dev)
+        arr = (C.c_void_p * _cabi.NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+        with torch.cuda.device(dev):
+            _cabi.check(lib.s2l_pack_weights(arr, _ptr(self.blob), self.uv_dims, self.out_ch, _stream()),
+                        "s2l_pack_weights")
+        self._keepalive = tensors
+        return self
+
+    @property
+    def device(self):
+        return self.blob.device
+
+
+# --------------------------------------------------------------------------------------- functional API
+def audio_encode(w, audio, frame_idx=None, want_latent=True, want_bias=True):
+    """AudioNet (+ per-frame MLP biases).  audio [F,16,29] or [F,29,16] -> (latent [F,64], frame_bias [F,4,256])."""
+    lib = _cabi.lib()
+    audio = _f32c(audio, "audio")
+    if audio.dim() != 3 or audio.shape[1] * audio.shape[2] != 16 * 29:
+        raise ValueError("audio must be [F,16,29] or [F,29,16], got %s" % (tuple(audio.shape),))
+    transposed = 1 if audio.shape[2] == 16 else 0         # tf_nerf.py:203-207
+    F = audio.shape[0]
+    idx = None
+    if frame_idx is not None:
+        idx = torch.as_tensor(frame_idx).to(device=audio.device, dtype=torch.int64).reshape(-1).contiguous()
+        if idx.numel() != F:
+            raise ValueError("frame_idx has %d entries for %d frames" % (idx.numel(), F))
+    latent = torch.empty(F, 64, device=audio.device) if want_latent else None
+    bias = torch.empty(F, 4, 256, device=audio.device) if want_bias else None
+    with torch.cuda.device(audio.device):
+        _cabi.check(lib.s2l_audio_encode_fwd(_ptr(w.blob), _ptr(audio), transposed, _ptr(idx), _ptr(latent), _ptr(bias),
+                                             F, w.uv_dims, w.out_ch, _stream()), "s2l_audio_encode_fwd")
+    return latent, bias
+
+
+def rgb_forward_rows(w, x, time_idx=None):
+    """General TalkingFace.rgb_forward contract (tf_nerf.py:225-285): x [N, uv_dims+64] with an arbitrary
+    latent per row, time_pts -> position[0].  fp32 exact path."""
+    lib = _cabi.lib()
+    x = _f32c(x, "uv_audio_pts")
+    if x.dim() != 2 or x.shape[1] != w.uv_dims + 64:
+        raise ValueError("uv_audio_pts must be [N,%d], got %s" % (w.uv_dims + 64, tuple(x.shape)))
+    out = torch.empty(x.shape[0], w.out_ch, device=x.device)
+    has_time = time_idx is not None
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_rgb_forward_rows(_ptr(w.blob), _ptr(x), x.shape[0], int(time_idx) if has_time else 0,
+                                             1 if has_time else 0, _ptr(out), w.uv_dims, w.out_ch, _stream()),
+                    "s2l_rgb_forward_rows")
+    return out
+
+
+def mlp_points(w, frame_bias, pts, precision="bf16x3"):
+    """rgb_forward on explicit points with per-frame-constant latent: pts [F,P,uv_dims] -> raw [F,P,out_ch]."""
+    lib = _cabi.lib()
+    pts = _f32c(pts, "pts")
+    F, P = pts.shape[0], pts.shape[1]
+    g = S2LGeom(n_frames=F, height=0, width=0, n_samples=0, pts_mode=_cabi.PTS_EXPLICIT, uv_dims=w.uv_dims,
+                out_ch=w.out_ch, z_per_ray=0, rays_per_frame_shared=0, pts_per_frame=P, eps_shift=0.0)
+    out = torch.empty(F, P, w.out_ch, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _cabi.check(lib.s2l_mlp_fwd(_ptr(w.blob), C.byref(g), _ptr(frame_bias), _ptr(pts), None, None, None, _ptr(out),
+                                    _cabi.PRECISIONS[precision], _stream()), "s2l_mlp_fwd")
+    return out
+
+
+def density2outputs(raw, z_vals, rays_d):
+    """rendering.py:30-62 (raw_noise_std = 0): raw [R,S,4], z_vals [R,S] or [S], rays_d [R,3]."""
+    lib = _cabi.lib()
+    raw = _f32c(raw, "raw")
+    z_vals = _f32c(z_vals, "z_vals")
+    rays_d = _f32c(rays_d, "rays_d")
+    R, S = raw.shape[0], raw.shape[1]
+    if raw.shape[2] != 4:
+        raise ValueError("raw must be [R,S,4]")
+    rgb = torch.empty(R, 3, device=raw.device)
+    weights = torch.empty(R, S, device=raw.device)
+    depth = torch.empty(R, device=raw.device)
+    with torch.cuda.device(raw.device):
+        _cabi.check(lib.s2l_composite_fwd(_ptr(raw), _ptr(z_vals), 1 if z_vals.dim() == 2 else 0, _ptr(rays_d), R, 0, S,
+                                          _ptr(rgb), _ptr(weights), _ptr(depth), _stream()), "s2l_composite_fwd")
+    return rgb, weights, depth
+
+
+def get_rays(H, W, focal, c2w):
+    """src/common.py:12-21: c2w [3,4] (or [4,4]) CUDA tensor -> rays_o, rays_d [H,W,3]."""
+    lib = _cabi.lib()
+    c = _f32c(c2w, "c2w")[:3, :4].contiguous()
+    ro = torch.empty(H, W, 3, device=c.device)
+    rd = torch.empty(H, W, 3, device=c.device)
+    with torch.cuda.device(c.device):
+        _cabi.check(lib.s2l_get_rays(_ptr(c), H, W, float(focal), _ptr(ro), _ptr(rd), _stream()), "s2l_get_rays")
+    return ro, rd
+
+
+class LipRenderer:
+    """Batched frame renderer over one PackedWeights blob.
+
+    render_frames(audio [F,16,29], index [F], H, W, mode=...) -> rgb [F,H,W,3]
+      mode="plain"      1 MLP eval / pixel                       (inference.py:144-159)
+      mode="ensemble4"  4 jittered taps / pixel, area blend      (training.py:158-251), eps_shift explicit
+      mode="volumetric" S samples / ray + alpha compositing      (uv_dims=3/out_ch=4 model)
+    Each frame uses its own index for the time code, i.e. the result equals calling the reference once
+    per frame (the reference's time PE only ever sees position[0], tf_nerf.py:439).
+    """
+
+    def __init__(self, weights, precision="bf16x3"):
+        if precision not in _cabi.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_cabi.PRECISIONS))
+        self.w = weights
+        self.precision = precision
+        self._scratch = None
+
+    def _scratch_for(self, geom, device):
+        need = _cabi.lib().s2l_render_scratch_bytes(C.byref(geom))
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._scratch
+
+    def render_frames(self, audio, index, H, W, mode="plain", eps_shift=0.0, n_samples=None, rays_o=None,
+                      rays_d=None, z_vals=None, out=None, return_aux=False, precision=None):
+        lib = _cabi.lib()
+        audio = _f32c(audio, "audio")
+        if audio.dim() != 3 or tuple(audio.shape[1:]) != (16, 29):
+            raise ValueError("audio must be [F,16,29], got %s" % (tuple(audio.shape),))
+        F = audio.shape[0]
+        dev = audio.device
+        idx = torch.as_tensor(index).to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        if idx.numel() != F:
+            raise ValueError("index has %d entries for %d frames" % (idx.numel(), F))
+        prec = _cabi.PRECISIONS[precision or self.precision]
+        g = S2LGeom(n_frames=F, height=H, width=W, n_samples=0, pts_mode=_cabi.PTS_GRID, uv_dims=self.w.uv_dims,
+                    out_ch=self.w.out_ch, z_per_ray=0, rays_per_frame_shared=0, pts_per_frame=0, eps_shift=float(eps_shift))
+        weights = depth = None
+        if mode == "plain":
+            g.pts_mode = _cabi.PTS_GRID
+        elif mode == "ensemble4":
+            g.pts_mode = _cabi.PTS_GRID_ENS4
+        elif mode == "volumetric":
+            g.pts_mode = _cabi.PTS_RAYS
+            if rays_o is None or rays_d is None or z_vals is None:
+                raise ValueError("volumetric mode needs rays_o, rays_d and z_vals")
+            rays_o = _f32c(rays_o, "rays_o").reshape(-1, 3)
+            rays_d = _f32c(rays_d, "rays_d").reshape(-1, 3)
+            z_vals = _f32c(z_vals, "z_vals")
+            R = H * W
+            if rays_o.shape[0] == R:
+                g.rays_per_frame_shared = 1
+            elif rays_o.shape[0] == R * F:
+                g.rays_per_frame_shared = 0
+            else:
+                raise ValueError("rays must be [H*W,3] or [F*H*W,3]")
+            if rays_d.shape != rays_o.shape:
+                raise ValueError("rays_o / rays_d shape mismatch")
+            if z_vals.dim() == 1:
+                g.z_per_ray = 0
+                g.n_samples = z_vals.shape[0]
+            else:
+                z_vals = z_vals.reshape(-1, z_vals.shape[-1])
+                if z_vals.shape[0] != R * F:
+                    raise ValueError("z_vals must be [S] or [F*H*W,S]")
+                g.z_per_ray = 1
+                g.n_samples = z_vals.shape[1]
+            if n_samples is not None and n_samples != g.n_samples:
+                raise ValueError("n_samples does not match z_vals")
+            if return_aux:
+                weights = torch.empty(F, R, g.n_samples, device=dev)
+                depth = torch.empty(F, R, device=dev)
+        else:
+            raise ValueError("unknown mode %r" % (mode,))
+        if out is None:
+            out = torch.empty(F, H, W, 3, device=dev)
+        else:
+            _need_cuda(out, "out")
+            if tuple(out.shape) != (F, H, W, 3) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous fp32 [F,H,W,3] tensor")
+        scratch = self._scratch_for(g, dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.s2l_render_frames(_ptr(self.w.blob), C.byref(g), _ptr(audio), _ptr(idx), _ptr(rays_o),
+                                              _ptr(rays_d), _ptr(z_vals), _ptr(out), _ptr(weights), _ptr(depth),
+                                              _ptr(scratch), prec, _stream()), "s2l_render_frames")
+        if return_aux:
+            return out, weights, depth
+        return out
+
+    def render_frames_host(self, audio_host, index_host, H, W, out_host=None, **kw):
+        """End-to-end call on HOST buffers: H2D of the audio windows / indices (pinned -> async), render,
+        D2H of the frames.  This is what bench.py times as `e2e`."""
+        dev = self.w.device
+        a = audio_host.to(dev, non_blocking=True)
+        i = index_host.to(dev, non_blocking=True)
+        rgb = self.render_frames(a, i, H, W, **kw)
+        if out_host is None:
+            out_host = torch.empty(rgb.shape, dtype=rgb.dtype, pin_memory=True)
+        out_host.copy_(rgb, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host

@@ -1,0 +1,256 @@
+"""Drop-in for the reference's `src.face_simple.models.tf_nerf.TalkingFace` (tf_nerf.py:12-389).
+
+Same constructor signature, attribute names, parameter names/shapes (115 state-dict keys for may.yaml)
+and method signatures, so `CheckpointIO.load` round-trips reference checkpoints and inference.py /
+train.py can call it unchanged (INTEGRATION.md shows the one-line import switch).
+
+Hot path (this repo's scope): audio_merge_forward and rgb_forward run the CUDA kernels behind the C ABI.
+Outside the hot path (SURVEY §8(f) "next"): post_fusion2_onlylip and the UNet are plain PyTorch modules
+kept only so that the checkpoint layout and the callers keep working.
+"""
+import os
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import renderer as R
+
+_HOT_PREFIXES = ("encoder_conv.", "encoder_fc1.", "fc_uv", "fc_audio", "fc_time", "pts_linears.", "output_linear.")
+
+
+def _conv_bn_relu_x2(cin, cout, cmid=None):
+    cmid = cmid or cout
+    return nn.Sequential(nn.Conv2d(cin, cmid, 3, padding=1, bias=False), nn.BatchNorm2d(cmid), nn.ReLU(inplace=True),
+                         nn.Conv2d(cmid, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class _Block(nn.Module):
+    def __init__(self, cin, cout, cmid=None):
+        super().__init__()
+        self.double_conv = _conv_bn_relu_x2(cin, cout, cmid)
+
+    def forward(self, x):
+        return self.double_conv(x)
+
+
+class _Down(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), _Block(cin, cout))
+
+    def forward(self, x):
+        return self.maxpool_conv(x)
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv = _Block(cin, cout, cin // 2)
+
+    def forward(self, lo, skip):
+        lo = self.up(lo)
+        dy, dx = skip.shape[2] - lo.shape[2], skip.shape[3] - lo.shape[3]
+        lo = F.pad(lo, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+        return self.conv(torch.cat([skip, lo], dim=1))
+
+
+class _Head(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class PostFusionUNet(nn.Module):
+    """State-dict-compatible stand-in for models/SimpleUnetLight.py:82-111 (2-down / 2-up UNet,
+    64-128-128 channels).  Out of the hot path; cuDNN through PyTorch."""
+
+    def __init__(self, cfg=None, n_channels=3, n_classes=3):
+        super().__init__()
+        c = 64
+        self.inc = _Block(n_channels, c)
+        self.down1 = _Down(c, 2 * c)
+        self.down2 = _Down(2 * c, 2 * c)
+        self.up1 = _Up(4 * c, c)
+        self.up2 = _Up(2 * c, c)
+        self.outc = _Head(c, n_classes)
+
+    def forward(self, x, x_level1=None, x_level2=None):
+        a = self.inc(x)
+        b = self.down1(a)
+        c = self.down2(b)
+        return self.outc(self.up2(self.up1(c, b), a))
+
+
+class TalkingFace(nn.Module):
+    def __init__(self, device, cfg, mode='train',
+                 use_viewdirs=False, coord_merge_audio=False,
+                 W=256, D=8, coord_D=4, skips=[4],
+                 uv_audio_dims=66, uv_dims=2, audio_dims=29, head_pose_dims=3,
+                 time_multires=10,
+                 output_ch=3, **args):
+        super().__init__()
+        m = cfg['model']
+        unsupported = [k for k in ('use_head_pose', 'use_lms', 'use_text', 'use_audio_mel', 'use_attention') if m.get(k)]
+        if unsupported or not m.get('audio_net', True) or not m.get('audio_not_embed', True) or not m.get('use_audio', True) \
+                or m.get('MLP_version') != 'v2' or not m.get('use_time', True) or W != 256 or D != 8 or list(skips) != [4] \
+                or int(m.get('uv_embed', 10)) != 10 or time_multires != 10:
+            raise NotImplementedError(
+                "speech2lip_b200.TalkingFace implements the may.yaml hot-path configuration (audio_net, "
+                "audio_not_embed, MLP v2, use_time, W=256, D=8, skips=[4], uv_embed=10); got unsupported options %s"
+                % (unsupported,))
+        self.cfg = cfg
+        self.device = device
+        self.use_viewdirs = use_viewdirs
+        self.coord_merge_audio = coord_merge_audio
+        self.uv_audio_dims = uv_audio_dims
+        self.use_attention = m['use_attention']
+        self.use_audio_net = m['audio_net']
+        self.use_uv_audio_sep = m.get('use_uv_audio_sep', True)
+        self.audio_not_embed = m['audio_not_embed']
+        self.skips = skips
+        self.uv_dims = uv_dims
+        self.audio_dims = 64                                 # tf_nerf.py:63-64 (audio_net)
+        self.head_pose_dims = head_pose_dims
+        self.use_audio = m['use_audio']
+        self.N_sample = cfg['training']['n_sample_points']   # read, never used (tf_nerf.py:44)
+        self.use_head_pose = m['use_head_pose']
+        self.use_head_pose_net = m.get('use_head_pose_net', False)
+        self.use_time = m['use_time']
+        self.use_post_fusion = m['use_post_fusion']
+        self.use_lms = m['use_lms']
+        self.use_text = m['use_text']
+        self.data_path = cfg['data']['path']
+        self.expand_lip_mask = m['expand_lip_mask']
+        self.MLP_version = m['MLP_version']
+        self.output_ch = output_ch
+        if self.use_post_fusion:
+            self.use_light_unet = m['use_light_unet']
+            self.use_resnet = m.get('use_resnet', False)
+            self.post_fusion_channel = m['post_fusion_channel']
+            self.post_fusion_unet = PostFusionUNet(cfg=cfg, n_channels=self.post_fusion_channel).to(device)
+
+        lrelu = lambda: nn.LeakyReLU(0.02, True)
+        self.encoder_conv = nn.Sequential(
+            nn.Conv1d(29, 32, 3, stride=2, padding=1), lrelu(), nn.Conv1d(32, 32, 3, stride=2, padding=1), lrelu(),
+            nn.Conv1d(32, 64, 3, stride=2, padding=1), lrelu(), nn.Conv1d(64, 64, 3, stride=2, padding=1), lrelu())
+        self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), lrelu(), nn.Linear(64, self.audio_dims))
+        # dead in every forward of the reference, but part of the checkpoint layout (tf_nerf.py:130-135)
+        self.coord_linears = nn.ModuleList([nn.Linear(2, W)] + [nn.Linear(W, W) for _ in range(coord_D - 1)]
+                                           + [nn.Linear(W, self.audio_dims)])
+        e = uv_dims + 2 * 10 * uv_dims
+        self.output_linear = nn.Linear(W, output_ch)
+        self.fc_uv = nn.Linear(e, W)
+        self.fc_uv_skip = nn.Linear(e, W)
+        self.fc_audio = nn.Linear(self.audio_dims, W)
+        self.fc_audio_skip = nn.Linear(self.audio_dims, W)
+        self.fc_time = nn.Linear(2 * time_multires, W)
+        self.fc_time_skip = nn.Linear(2 * time_multires, W)
+        self.pts_linears = nn.ModuleList([nn.Linear(W, W)] + [nn.Linear(W, W) if i not in skips else nn.Linear(2 * W, W)
+                                                              for i in range(D - 1)])
+        if m['use_canonical_depth']:
+            if 'canonical_depth_init_path' in m:
+                init = torch.from_numpy(np.load(m['canonical_depth_init_path'])).float()
+                depth = init.clone()
+                depth[depth == 0] = depth[depth > 0].mean()
+                import cv2
+                mask = cv2.imread(os.path.join(cfg['data']['path'], 'canonical_head_mask.jpg')) / 255
+                mask[mask > 0] = 1
+                depth[torch.from_numpy(mask[:, :, 0]).int() == 0] = 0
+                depth[init > 0] = init[init > 0]
+            else:
+                depth = torch.randn((m['canonical_depth_height'], m['canonical_depth_width']))
+            self.canonical_depth_head = nn.Parameter(depth, requires_grad=True)
+        self._packed = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ packed weights (kernel layout)
+    def _hot_params(self):
+        return {k: v for k, v in self.state_dict(keep_vars=True).items() if k.startswith(_HOT_PREFIXES)}
+
+    def packed_weights(self):
+        """PackedWeights for the current parameter values; re-packed when any hot-path tensor changed
+        (in-place optimizer steps and load_state_dict bump tensor._version)."""
+        hp = self._hot_params()
+        key = tuple((v.data_ptr(), v._version) for v in hp.values())
+        if self._packed is None or key != self._packed_key:
+            if self._packed is None:
+                self._packed = R.PackedWeights(hp, self.uv_dims, self.output_ch)
+            else:
+                self._packed.repack(hp)
+            self._packed_key = key
+        return self._packed
+
+    def _check_inference(self, *tensors):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._hot_params().values()):
+            raise NotImplementedError(
+                "speech2lip_b200.TalkingFace: backward of the fused MLP is not built yet (SURVEY §8(f) rank 2); "
+                "call the hot path under torch.no_grad()")
+
+    # ------------------------------------------------------------------ hot path
+    def audio_merge_forward(self, audio):
+        """tf_nerf.py:197-213.  audio: [B,16,29] or [B,29,16] -> [B,64]."""
+        self._check_inference()
+        latent, _ = R.audio_encode(self.packed_weights(), audio, None, want_latent=True, want_bias=False)
+        return latent
+
+    def rgb_forward(self, uv_audio_pts, time_pts=None, head_pose_pts=None, rgb_pts=None, lms_pts=None, text_pts=None):
+        """tf_nerf.py:225-285.  uv_audio_pts [N, uv_dims+64]; time_pts: only element 0 is used (tf_nerf.py:439)."""
+        self._check_inference()
+        t = None
+        if time_pts is not None:
+            t = int(torch.as_tensor(time_pts).reshape(-1)[0].item())
+        return R.rgb_forward_rows(self.packed_weights(), uv_audio_pts, t)
+
+    def renderer(self, precision="bf16x3"):
+        """Batched frame renderer (not expressible through the reference's per-call contract)."""
+        return R.LipRenderer(self.packed_weights(), precision)
+
+    # ------------------------------------------------------------------ outside the hot path (PyTorch)
+    def post_fusion2_onlylip(self, rgb_lip_warped, rgb_face_canonical, rgb_gt, mask_lip_canonical, lip_lefttop_x,
+                             lip_lefttop_y, coord, use_canonical_space=False, change_pose=-1, mask_face_canonical=None,
+                             wav2lip=None, mask_head_observed=None, use_post_fusion_blackaug=False):
+        """tf_nerf.py:287-389 (light-UNet branch): paste lip crop into the canonical face, warp canonical ->
+        observed with `coord`, optional black-hole augmentation, UNet refine.  [B,H,W,C] layouts."""
+        if not self.use_light_unet:
+            return None
+        h, w = rgb_face_canonical.shape[1:3]
+        lh, lw = rgb_lip_warped.shape[1:3]
+        x0, y0 = int(lip_lefttop_x), int(lip_lefttop_y)
+        left, up = x0 - 1, y0 - 1
+        right, down = w - (left + lw), h - (up + lh)
+        shifted = any(s in self.data_path for s in ('macron', 'obama_adnerf', 'obama2_face_crop', 'may'))
+        pad = (left + 1, right - 1, up + 1, down - 1) if shifted else (left, right, up, down)
+        lip_full = F.pad(rgb_lip_warped.permute(0, 3, 1, 2), pad=pad, mode='constant', value=0).permute(0, 2, 3, 1)
+        merged_canonical = mask_lip_canonical * lip_full + (1 - mask_lip_canonical) * rgb_face_canonical
+        mask = mask_lip_canonical
+        if self.expand_lip_mask:
+            p = lw // 12 if 'obama2_face_crop' in self.data_path else lw // 5
+            mask = torch.zeros_like(mask_lip_canonical)
+            mask[:, y0 - p:y0 + lh + 2 * p, x0 - p:x0 + lw + p, :] = 1
+        merged = F.grid_sample(merged_canonical.permute(0, 3, 1, 2), coord, align_corners=False)
+        mask_obs = F.grid_sample(mask.float().permute(0, 3, 1, 2), coord, align_corners=False)
+        mask_obs = (mask_obs != 0).int()
+        gt = rgb_gt.permute(0, 3, 1, 2)
+        if use_post_fusion_blackaug and random.random() > 0.5:
+            face_obs = F.grid_sample((rgb_face_canonical > 0).float().permute(0, 3, 1, 2), coord, align_corners=False)
+            face_obs = (face_obs == 1).float()
+
+            def holes(ref):
+                keep = (torch.randn(ref.shape, device=ref.device)[:, :1] >= 0.000001).float()
+                keep = keep * face_obs + (1 - face_obs)
+                return (keep != 0).float()
+
+            n1, n2 = holes(merged), holes(gt)
+            before = merged.clone()
+            merged = n1 * before + (1 - n1) * gt
+            gt = n2 * gt + (1 - n2) * before
+        fused_in = mask_obs * merged + (1 - mask_obs) * gt
+        recon = self.post_fusion_unet(fused_in)
+        return recon.permute(0, 2, 3, 1), fused_in.permute(0, 2, 3, 1), merged_canonical

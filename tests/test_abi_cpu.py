@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads, exports every symbol include/speech2lip_b200.h declares, and rejects
+bad arguments before touching the GPU.  No compute calls here."""
+import ctypes as C
+import json
+import math
+import os
+import re
+
+import pytest
+import torch
+
+from speech2lip_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "speech2lip_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2l_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.lib()
+    names = header_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "libs2l_b200.so does not export %s" % n
+    assert sorted(_cabi.SYMBOLS) == names, "binding table and header disagree"
+    assert lib.s2l_abi_version() == 1
+
+
+def test_param_order_matches_header_enum():
+    src = open(os.path.join(ROOT, "include", "speech2lip_b200.h")).read()
+    assert "S2L_NUM_PARAMS" in src
+    assert _cabi.NUM_PARAMS == 42 and len(_cabi.PARAM_NAMES) == 42
+    assert _cabi.PARAM_NAMES[0] == "encoder_conv.0.weight" and _cabi.PARAM_NAMES[12] == "fc_uv.weight"
+    assert _cabi.PARAM_NAMES[24] == "pts_linears.0.weight" and _cabi.PARAM_NAMES[40] == "output_linear.weight"
+
+
+def test_blob_size_and_div_term():
+    lib = _cabi.lib()
+    n = lib.s2l_blob_bytes(2, 3)
+    assert 4_000_000 < n < 8_000_000 and n % 1024 == 0
+    buf = (C.c_float * 10)()
+    lib.s2l_time_div_term(buf)
+    ref = torch.exp(torch.arange(0, 20, 2, dtype=torch.float) * -(math.log(10000.0) / 20))   # tf_nerf.py:431-432
+    assert torch.equal(torch.tensor(list(buf)), ref)
+
+
+def test_errors_are_reported_not_crashed():
+    lib = _cabi.lib()
+    assert lib.s2l_pack_weights(None, None, 2, 3, None) != 0
+    assert b"null" in lib.s2l_last_error()
+    arr = (C.c_void_p * _cabi.NUM_PARAMS)()
+    assert lib.s2l_pack_weights(arr, C.c_void_p(16), 5, 3, None) != 0
+    assert b"uv_dims" in lib.s2l_last_error()
+    g = _cabi.S2LGeom(n_frames=1, height=4, width=4, n_samples=0, pts_mode=_cabi.PTS_RAYS, uv_dims=2, out_ch=3)
+    assert lib.s2l_render_frames(C.c_void_p(16), C.byref(g), C.c_void_p(16), None, None, None, None, C.c_void_p(16),
+                                 None, None, C.c_void_p(16), 1, None) != 0
+    assert b"ray mode" in lib.s2l_last_error()
+    g.pts_mode = 9
+    assert lib.s2l_mlp_fwd(C.c_void_p(16), C.byref(g), C.c_void_p(16), None, None, None, None, C.c_void_p(16), 0, None) != 0
+    assert lib.s2l_composite_fwd(C.c_void_p(16), C.c_void_p(16), 0, C.c_void_p(16), 4, 0, 0, C.c_void_p(16), None, None, None) != 0
+    with pytest.raises(RuntimeError):
+        _cabi.check(3, "demo")
+
+
+def test_no_fallback_for_cpu_tensors():
+    from speech2lip_b200 import renderer as R
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        R._f32c(torch.zeros(3), "x")
+
+
+def test_talking_face_state_dict_matches_reference_layout():
+    """115 keys with the reference's names and shapes (SURVEY §8(b) checkpoint layout)."""
+    from speech2lip_b200 import TalkingFace
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    for tag, (uvd, och) in {"live": (2, 3), "volumetric": (3, 4)}.items():
+        m = TalkingFace(device=torch.device("cpu"), cfg=cfg, uv_dims=uvd, output_ch=och)
+        mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert mine == keys[tag]
+    assert len(keys["live"]) == 115
+    assert m.audio_dims == 64 and hasattr(m, "post_fusion_unet") and hasattr(m, "canonical_depth_head")
+    bad = json.loads(json.dumps(cfg))
+    bad["model"]["MLP_version"] = "v1"
+    with pytest.raises(NotImplementedError):
+        TalkingFace(device=torch.device("cpu"), cfg=bad)
+
+
+def test_post_fusion_runs_on_cpu():
+    """outside the hot path, plain PyTorch: shapes only (tf_nerf.py:287-389)."""
+    from speech2lip_b200 import TalkingFace
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = TalkingFace(device=torch.device("cpu"), cfg=cfg, mode="eval").eval()
+    B, H, W, lh, lw = 1, 64, 64, 8, 12
+    lip = torch.rand(B, lh, lw, 3)
+    face = torch.rand(B, H, W, 3)
+    mask = torch.zeros(B, H, W, 1)
+    mask[:, 21:29, 21:33] = 1
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+    coord = torch.stack([xs, ys], -1)[None]
+    with torch.no_grad():
+        recon, merged, canon = m.post_fusion2_onlylip(lip, face, face.clone(), mask, 20, 20, coord)
+    assert recon.shape == (B, H, W, 3) and merged.shape == (B, H, W, 3) and canon.shape == (B, H, W, 3)

@@ -1,0 +1,55 @@
+"""CPU, gloo, world_size 2: the multi-GPU host logic (frame sharding + one parameter broadcast)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_frames_partitions_exactly():
+    from speech2lip_b200.dist import shard_frames
+    for n in (0, 1, 7, 8, 125, 1000):
+        for world in (1, 2, 4, 8):
+            spans = [shard_frames(n, r, world) for r in range(world)]
+            covered = [i for lo, hi in spans for i in range(lo, hi)]
+            assert covered == list(range(n))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= (n + world - 1) // world
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import synth
+    from speech2lip_b200.dist import broadcast_params, gather_frames, shard_frames
+    # rank 0 holds the real weights, rank 1 garbage: after ONE broadcast both must agree
+    sd = {k: torch.from_numpy(v).clone() for k, v in synth.make_state_dict(seed=rank, kind="default").items()}
+    broadcast_params(sd, src=0)
+    ref = synth.make_state_dict(seed=0, kind="default")
+    same = all(torch.equal(sd[k], torch.from_numpy(ref[k])) for k in ref)
+    lo, hi = shard_frames(5, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1, 1).expand(-1, 2, 2, 3).contiguous()
+    full = gather_frames(local, 5)
+    ok_gather = torch.equal(full[:, 0, 0, 0], torch.arange(5, dtype=torch.float32))
+    q.put((rank, same, ok_gather, (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_broadcast_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1], "parameters differ after broadcast"
+    assert res[0][2] and res[1][2], "gather_frames lost frame order"
+    assert res[0][3] == (0, 3) and res[1][3] == (3, 5)

@@ -1,0 +1,344 @@
+"""GPU (B200) parity tests: the CUDA path, called through the C ABI, against
+ (1) the golden vectors produced by the REAL reference (tests/golden/reference_golden.npz),
+ (2) the oracle (oracle/s2l_oracle.py) on seeded inputs at sizes it finishes in seconds,
+ (3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star: <= 1e-3 max-abs fp32 per pixel, PSNR within 0.05 dB):
+  fp32 exact path   2e-5 (default init) / 2e-4 (kaiming, O(1)..O(10) outputs)
+  bf16x3 parity path 1e-3 max-abs on every case, including the kaiming ("trained-like") weights
+  bf16x1 fast path   reported, only sanity-bounded (it is NOT a parity mode)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import s2l_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PARITY_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def S():
+    import speech2lip_b200 as s2l
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert os.path.exists(s2l.LIB_PATH), "CUDA extension missing: no fallback exists"
+    return s2l
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+_cache = {}
+
+
+def packed(S, kind, uvd=2, och=3, seed=0):
+    key = (kind, uvd, och, seed)
+    if key not in _cache:
+        sd = {k: torch.from_numpy(v).to(dev()) for k, v in synth.make_state_dict(seed, kind, uvd, och).items()}
+        _cache[key] = S.PackedWeights(sd, uvd, och)
+    return _cache[key]
+
+
+def osd(kind, uvd=2, och=3, seed=0, dtype=torch.float32):
+    return O.to_torch_sd(synth.make_state_dict(seed, kind, uvd, och), dtype)
+
+
+def maxabs(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).max())
+
+
+def tol_fp32(kind):
+    return 2e-5 if kind == "default" else 3e-4
+
+
+# ------------------------------------------------------------------------------------------ a1 AudioNet
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+def test_audio_net_vs_golden(S, golden, kind):
+    g = golden["audio_%s" % kind]
+    w = packed(S, kind)
+    lat, bias = S.audio_encode(w, torch.from_numpy(g["audio"]).to(dev()), torch.arange(4))
+    assert maxabs(lat.cpu(), g["latent"]) < 2e-6
+    lat_t, _ = S.audio_encode(w, torch.from_numpy(g["audio"]).permute(0, 2, 1).contiguous().to(dev()), None)
+    assert maxabs(lat_t.cpu(), g["latent_from_29x16"]) < 2e-6
+    # per-frame biases against the oracle's pieces (tf_nerf.py:252-258, 268-276)
+    sd = osd(kind)
+    a = torch.from_numpy(g["latent"])
+    for f in range(4):
+        t = O.time_embed(torch.tensor([f]))
+        b0 = sd["fc_uv.bias"] + torch.nn.functional.linear(a[f], sd["fc_audio.weight"], sd["fc_audio.bias"]) \
+            + torch.nn.functional.linear(t, sd["fc_time.weight"], sd["fc_time.bias"])
+        bs = sd["fc_uv_skip.bias"] + torch.nn.functional.linear(a[f], sd["fc_audio_skip.weight"], sd["fc_audio_skip.bias"]) \
+            + torch.nn.functional.linear(t, sd["fc_time_skip.weight"], sd["fc_time_skip.bias"])
+        assert maxabs(bias[f, 0].cpu(), b0) < 5e-6
+        assert maxabs(bias[f, 1].cpu(), bs) < 5e-6
+        f0 = torch.nn.functional.linear(b0.double(), sd["pts_linears.0.weight"].double(), sd["pts_linears.0.bias"].double())
+        f5 = torch.nn.functional.linear(bs.double(), sd["pts_linears.5.weight"][:, :256].double(), sd["pts_linears.5.bias"].double())
+        assert maxabs(bias[f, 2].cpu(), f0) < 2e-5
+        assert maxabs(bias[f, 3].cpu(), f5) < 2e-5
+
+
+def test_audio_batch_tiling_invariance(S):
+    """inference.py:144 tiles the same window N times; every copy must give the identical latent."""
+    w = packed(S, "default")
+    a = torch.from_numpy(synth.make_audio(1, seed=3)).to(dev())
+    l1, _ = S.audio_encode(w, a, None)
+    ln, _ = S.audio_encode(w, a.tile(777, 1, 1), None)
+    assert torch.equal(ln, l1.expand(777, -1))
+
+
+# ------------------------------------------------------------------------------------------ a4 + inference loop body
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+@pytest.mark.parametrize("shape", [(24, 32, 5), (8, 8, 6000)])
+def test_plain_vs_golden(S, golden, kind, shape, precision):
+    H, W, idx = shape
+    g = golden["plain_%s_%dx%d_i%d" % (kind, H, W, idx)]
+    r = S.LipRenderer(packed(S, kind), precision)
+    rgb = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([idx]), H, W, mode="plain")
+    err = maxabs(rgb[0].cpu(), g["rgb"])
+    print("plain %s %s %s maxabs %.3e (output absmax %.3f)" % (kind, shape, precision, err, np.abs(g["rgb"]).max()))
+    assert err < (tol_fp32(kind) if precision == "fp32" else PARITY_TOL)
+    if precision == "bf16x3":
+        assert O.psnr(rgb[0].cpu(), torch.from_numpy(g["rgb"])) > 60.0, "render PSNR vs reference too low"
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+def test_fast_mode_is_sane_but_not_parity(S, golden, kind):
+    g = golden["plain_%s_24x32_i5" % kind]
+    r = S.LipRenderer(packed(S, kind), "bf16x1")
+    rgb = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([5]), 24, 32, mode="plain")
+    err = maxabs(rgb[0].cpu(), g["rgb"])
+    scale = float(np.abs(g["rgb"]).max())
+    print("bf16x1 %s maxabs %.3e (scale %.3f)" % (kind, err, scale))
+    assert err < 0.1 * max(scale, 1e-3) + 1e-3
+
+
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+def test_rgb_forward_rows_general_contract(S, golden, kind):
+    """arbitrary latent per row (tf_nerf.py:225-285): fp32 exact path."""
+    g = golden["rowlatent_%s" % kind]
+    out = S.rgb_forward_rows(packed(S, kind), torch.from_numpy(g["x"]).to(dev()), int(g["index"]))
+    assert maxabs(out.cpu(), g["out"]) < tol_fp32(kind)
+
+
+# ------------------------------------------------------------------------------------------ a5 local ensemble
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+@pytest.mark.parametrize("seed", [11, 12])
+def test_ensemble4_vs_golden(S, golden, kind, seed, precision):
+    g = golden["ens4_%s_seed%d" % (kind, seed)]
+    H, W = int(g["H"]), int(g["W"])
+    # RNG-aligned: draw eps exactly as training.py:198-200 does, on the device the model lives on is not
+    # reproducible across device types, so the CPU draw of the golden run is replayed here
+    torch.manual_seed(seed)
+    eps = float(((0.5 / H) * torch.rand(1) / 2.0).item())
+    assert eps == float(g["eps"][0])
+    r = S.LipRenderer(packed(S, kind), precision)
+    rgb = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([int(g["index"])]), H, W,
+                          mode="ensemble4", eps_shift=eps)
+    err = maxabs(rgb[0].cpu(), g["rgb"])
+    print("ens4 %s seed %d %s maxabs %.3e" % (kind, seed, precision, err))
+    assert err < (tol_fp32(kind) if precision == "fp32" else PARITY_TOL)
+
+
+def test_ensemble4_weights_sum_to_one(S):
+    """property: with a constant MLP the 4-tap blend must return that constant."""
+    sd = {k: torch.from_numpy(v).to(dev()) for k, v in synth.make_state_dict(0, "default").items()}
+    sd["output_linear.weight"] = torch.zeros_like(sd["output_linear.weight"])
+    sd["output_linear.bias"] = torch.tensor([0.25, -1.5, 3.0], device=dev())
+    r = S.LipRenderer(S.PackedWeights(sd), "bf16x3")
+    a = torch.from_numpy(synth.make_audio(2, seed=4)).to(dev())
+    rgb = r.render_frames(a, torch.tensor([0, 1]), 13, 9, mode="ensemble4", eps_shift=0.01)
+    want = torch.tensor([0.25, -1.5, 3.0], device=dev()).expand(2, 13, 9, 3)
+    assert (rgb - want).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ a7/a8 + volumetric
+def test_get_rays_and_composite_vs_golden(S, golden):
+    g = golden["vol_default_8x8x16"]
+    ro, rd = S.get_rays(8, 8, float(g["focal"]), torch.from_numpy(g["c2w"]).to(dev()))
+    assert maxabs(ro.reshape(-1, 3).cpu(), g["rays_o"]) == 0.0
+    assert maxabs(rd.reshape(-1, 3).cpu(), g["rays_d"]) < 1e-7
+    c = golden["composite_only"]
+    rgb, w, d = S.density2outputs(torch.from_numpy(c["raw"]).to(dev()), torch.from_numpy(c["z"]).to(dev()),
+                                  torch.from_numpy(c["rays_d"]).to(dev()))
+    assert maxabs(rgb.cpu(), c["rgb"]) < 2e-6
+    assert maxabs(w.cpu(), c["weights"]) < 2e-6
+    assert maxabs(d.cpu(), c["depth"]) < 2e-6
+    assert (w.sum(-1) <= 1 + 1e-5).all() and (w >= 0).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+@pytest.mark.parametrize("shape", [(8, 8, 16), (6, 10, 64)])
+def test_volumetric_vs_golden(S, golden, kind, shape, precision):
+    H, W, Sn = shape
+    g = golden["vol_%s_%dx%dx%d" % (kind, H, W, Sn)]
+    r = S.LipRenderer(packed(S, kind, 3, 4), precision)
+    z = torch.linspace(0., 1., Sn).to(dev())
+    rgb, weights, depth = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([int(g["index"])]), H, W,
+                                          mode="volumetric", rays_o=torch.from_numpy(g["rays_o"]).to(dev()),
+                                          rays_d=torch.from_numpy(g["rays_d"]).to(dev()), z_vals=z, return_aux=True)
+    e_rgb, e_w, e_d = maxabs(rgb[0].cpu(), g["rgb"]), maxabs(weights[0].cpu(), g["weights"]), maxabs(depth[0].cpu(), g["depth"])
+    print("vol %s %s %s rgb %.3e weights %.3e depth %.3e" % (kind, shape, precision, e_rgb, e_w, e_d))
+    tol = tol_fp32(kind) if precision == "fp32" else PARITY_TOL
+    assert e_rgb < tol and e_w < tol and e_d < tol
+    # per-ray z_vals [R,S] and per-frame rays [F*R,3] give the same result as the shared forms
+    rgb2 = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([int(g["index"])]), H, W, mode="volumetric",
+                           rays_o=torch.from_numpy(g["rays_o"]).to(dev()), rays_d=torch.from_numpy(g["rays_d"]).to(dev()),
+                           z_vals=z.expand(H * W, Sn).contiguous())
+    assert torch.equal(rgb2, rgb)
+
+
+# ------------------------------------------------------------------------------------------ oracle at seeded mid sizes
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_plain_vs_oracle_trained_like_80x120(S, precision):
+    """the reference's native lip size (may.yaml:7-8), 'trained-like' weights, 3 frames incl. a large index."""
+    H, W = 80, 120
+    audio = torch.from_numpy(synth.make_audio(3, seed=7))
+    idx = [0, 17, 5999]
+    sd = osd("trained")
+    want = torch.stack([O.render_plain(sd, audio[i:i + 1], idx[i], H, W) for i in range(3)])
+    r = S.LipRenderer(packed(S, "trained"), precision)
+    got = r.render_frames(audio.to(dev()), torch.tensor(idx), H, W, mode="plain").cpu()
+    err = maxabs(got, want)
+    psnr = O.psnr(got, want)
+    print("80x120 trained-like %s maxabs %.3e psnr %.1f dB" % (precision, err, psnr))
+    assert err < (3e-4 if precision == "fp32" else PARITY_TOL)
+    assert psnr > 70.0
+
+
+def test_errors_vs_fp64_truth(S):
+    """rank the errors: |cuda - fp64 truth| for the parity path must be comparable to |fp32 reference - truth|."""
+    H, W = 32, 32
+    audio = torch.from_numpy(synth.make_audio(1, seed=8))
+    truth = O.render_plain(osd("kaiming", dtype=torch.float64), audio.double(), 3, H, W)
+    ref32 = O.render_plain(osd("kaiming"), audio, 3, H, W)
+    for prec in ("fp32", "bf16x3", "bf16x1"):
+        got = S.LipRenderer(packed(S, "kaiming"), prec).render_frames(audio.to(dev()), torch.tensor([3]), H, W).cpu()[0]
+        print("%-7s |cuda-truth| %.3e   |ref32-truth| %.3e   |cuda-ref32| %.3e" % (
+            prec, maxabs(got, truth), maxabs(ref32, truth), maxabs(got, ref32)))
+        if prec != "bf16x1":
+            assert maxabs(got, truth) < PARITY_TOL
+
+
+# ------------------------------------------------------------------------------------------ edges the domain has
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_ragged_sizes_and_empty(S, precision):
+    r = S.LipRenderer(packed(S, "default"), precision)
+    sd = osd("default")
+    for (H, W) in ((1, 1), (7, 5), (3, 43), (9, 15)):          # not multiples of the 64/128-point tiles
+        audio = torch.from_numpy(synth.make_audio(2, seed=H * 100 + W))
+        got = r.render_frames(audio.to(dev()), torch.tensor([4, 9]), H, W).cpu()
+        want = torch.stack([O.render_plain(sd, audio[i:i + 1], [4, 9][i], H, W) for i in range(2)])
+        assert maxabs(got, want) < (2e-5 if precision == "fp32" else PARITY_TOL), (H, W)
+    empty = r.render_frames(torch.zeros(0, 16, 29, device=dev()), torch.zeros(0, dtype=torch.int64), 8, 8)
+    assert empty.shape == (0, 8, 8, 3)
+    with pytest.raises(ValueError):
+        r.render_frames(torch.zeros(2, 16, 28, device=dev()), torch.tensor([0, 1]), 8, 8)
+    with pytest.raises(ValueError):
+        r.render_frames(torch.zeros(2, 16, 29, device=dev()), torch.tensor([0]), 8, 8)
+
+
+@pytest.mark.parametrize("Sn", [1, 3, 48, 200])
+def test_volumetric_odd_sample_counts(S, Sn):
+    """S = 1, non-powers of two, and S larger than a 128-point tile (rays straddle tiles)."""
+    H, W = 5, 7
+    sdv = osd("kaiming", 3, 4)
+    audio = torch.from_numpy(synth.make_audio(1, seed=9))
+    c2w = torch.eye(4)[:3]
+    want = O.render_volumetric(sdv, audio, 2, H, W, Sn, 10.0, c2w)
+    ro, rd = O.get_rays(H, W, 10.0, c2w)
+    r = S.LipRenderer(packed(S, "kaiming", 3, 4), "bf16x3")
+    got = r.render_frames(audio.to(dev()), torch.tensor([2]), H, W, mode="volumetric", rays_o=ro.reshape(-1, 3).to(dev()),
+                          rays_d=rd.reshape(-1, 3).to(dev()), z_vals=O.z_samples(Sn).to(dev())).cpu()[0]
+    assert maxabs(got, want) < PARITY_TOL
+
+
+def test_frames_are_independent_and_deterministic(S):
+    """a frame's pixels depend only on (weights, its window, its index): batch == one-by-one, bit-exact,
+    and repeated launches are bit-identical (no atomics / order dependence)."""
+    r = S.LipRenderer(packed(S, "kaiming"), "bf16x3")
+    audio = torch.from_numpy(synth.make_audio(5, seed=10)).to(dev())
+    idx = torch.tensor([3, 1, 4, 1, 5])
+    batch = r.render_frames(audio, idx, 16, 24)
+    again = r.render_frames(audio, idx, 16, 24)
+    assert torch.equal(batch, again)
+    for i in range(5):
+        one = r.render_frames(audio[i:i + 1], idx[i:i + 1], 16, 24)
+        assert torch.equal(one[0], batch[i])
+    assert not torch.equal(batch[1], batch[2])
+
+
+# ------------------------------------------------------------------------------------------ full BASELINE sizes
+def test_full_size_256x256x64_properties(S):
+    """BASELINE.json config 2 geometry (one frame of it): 256x256 rays x 64 samples = 4.19 M point evals.
+    (a) tensor-core parity path vs the fp32 exact path on the GPU over ALL rays; (b) oracle on a random
+    subset of rays; (c) compositing invariants."""
+    H = W = 256
+    Sn = 64
+    audio = torch.from_numpy(synth.make_audio(1, seed=11))
+    c2w = torch.eye(4)[:3].clone()
+    ro, rd = O.get_rays(H, W, 1200.0, c2w)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    z = O.z_samples(Sn)
+    w = packed(S, "kaiming", 3, 4)
+    out = {}
+    for prec in ("fp32", "bf16x3"):
+        rgb, weights, depth = S.LipRenderer(w, prec).render_frames(
+            audio.to(dev()), torch.tensor([12]), H, W, mode="volumetric", rays_o=ro.to(dev()), rays_d=rd.to(dev()),
+            z_vals=z.to(dev()), return_aux=True)
+        out[prec] = (rgb, weights, depth)
+    e = (out["fp32"][0] - out["bf16x3"][0]).abs().max().item()
+    print("256x256x64: tc-vs-fp32 maxabs %.3e" % e)
+    assert e < PARITY_TOL
+    wsum = out["bf16x3"][1].sum(-1)
+    assert (wsum <= 1 + 1e-4).all() and (out["bf16x3"][1] >= 0).all()
+    assert torch.isfinite(out["bf16x3"][0]).all()
+    # oracle on 96 random rays
+    gsel = torch.Generator().manual_seed(0)
+    sel = torch.randperm(H * W, generator=gsel)[:96]
+    sdv = osd("kaiming", 3, 4)
+    pts = ro[sel][:, None, :] + rd[sel][:, None, :] * z[None, :, None]
+    lat = O.audio_merge_forward(sdv, audio)
+    x = torch.cat([pts.reshape(-1, 3), lat.expand(96 * Sn, -1)], -1)
+    raw = O.rgb_forward(sdv, x, torch.tensor([12]), uv_dims=3).reshape(96, Sn, 4)
+    want, _, _ = O.density2outputs(raw, z.expand(96, Sn), rd[sel])
+    got = out["bf16x3"][0][0].reshape(-1, 3)[sel.to(dev())].cpu()
+    assert maxabs(got, want) < PARITY_TOL
+
+
+# ------------------------------------------------------------------------------------------ drop-in module
+def test_talking_face_drop_in(S, golden):
+    """the nn.Module surface inference.py uses (inference.py:95-159), fed a reference-layout checkpoint."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval").to(dev()).eval()
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming").items()}
+    missing = m.load_state_dict(sd, strict=False)          # CheckpointIO loads strict=False (checkpoints.py:106)
+    assert not missing.unexpected_keys
+    g = golden["plain_kaiming_24x32_i5"]
+    H, W = 24, 32
+    with torch.no_grad():
+        audio = torch.from_numpy(g["audio"]).to(dev()).tile(H * W, 1, 1)              # inference.py:144
+        coords = torch.from_numpy(O.get_coords(W, H).numpy()).to(dev())
+        ab = m.audio_merge_forward(audio)
+        x = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, 66)
+        out = m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()), rgb_pts=None)
+    assert maxabs(out[:, :3].reshape(H, W, 3).cpu(), g["rgb"]) < tol_fp32("kaiming")
+    # weights changed in place -> repack is automatic
+    with torch.no_grad():
+        m.output_linear.bias.add_(1.0)
+        out2 = m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()))
+    assert abs((out2 - out).mean().item() - 1.0) < 1e-5
+    with pytest.raises(NotImplementedError):
+        m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()))        # grad mode: backward not built yet
+    rgb = m.renderer("bf16x3").render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([5]), H, W)
+    assert maxabs((rgb[0] - 1.0).cpu(), g["rgb"]) < PARITY_TOL
