@@ -131,10 +131,10 @@ extern "C" int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, cons
                                      const float* rays_o, const float* rays_d, const float* z_vals, float* rgb,
                                      float* weights, float* depth, void* scratch, int32_t precision, void* stream) {
   if (int e = validate_geom(geom, "s2l_render_frames")) return e;
+  if (geom->n_frames == 0 || points_per_frame(*geom) == 0) return 0;      /* empty batch: nothing to do */
   if (!blob || !audio || !rgb || !scratch) { set_error("s2l_render_frames: null blob/audio/rgb/scratch"); return 1; }
   if (geom->pts_mode == S2L_PTS_EXPLICIT) { set_error("s2l_render_frames: EXPLICIT points are served by s2l_mlp_fwd"); return 2; }
   if (geom->pts_mode == S2L_PTS_RAYS && geom->out_ch != 4) { set_error("s2l_render_frames: ray mode needs the out_ch=4 model"); return 2; }
-  if (geom->n_frames == 0 || points_per_frame(*geom) == 0) return 0;
   float* bias = reinterpret_cast<float*>(scratch);
   const size_t bias_bytes = (((size_t)geom->n_frames * 4 * 256 * sizeof(float)) + 255) & ~size_t(255);
   float* raw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + bias_bytes);

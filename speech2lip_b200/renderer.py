@@ -236,6 +236,8 @@ class LipRenderer:
             raise ValueError("unknown mode %r" % (mode,))
         if out is None:
             out = torch.empty(F, H, W, 3, device=dev)
+            if F == 0 or H * W == 0:
+                return (out, weights, depth) if return_aux else out
         else:
             _need_cuda(out, "out")
             if tuple(out.shape) != (F, H, W, 3) or out.dtype != torch.float32 or not out.is_contiguous():
