@@ -7,7 +7,7 @@
 //                 time div_term, folded input weights fold0 = W0*Wuv, fold5 = W5a*Wuv_skip
 //   FP32    fp32  exact-path weights, transposed to [K][256] so a K-chunk is one contiguous 16 KB run
 //   TCBIAS  fp32  per-layer bias rows for the tensor-core path
-//   TCW     bf16  tensor-core B-operand "granules": [64 rows x 64 K] tiles stored as the exact
+//   TCW     bf16  tensor-core B-operand "granules": [128 rows x 64 K] tiles stored as the exact
 //                 shared-memory image the tcgen05 descriptor expects (K-major, 128-byte swizzle),
 //                 hi plane then lo plane (bf16 split of the fp32 weight), in MMA issue order so the
 //                 producer streams them with plain 1-D bulk copies (UBLKCP), no tensor map.
@@ -66,20 +66,20 @@ constexpr int F_OUT_B    = F_OUT_W + 4 * 256;            // [4]
 constexpr int F_TOTAL    = F_OUT_B + 4;
 
 // ---- TCW section (byte offsets inside the section)
-constexpr int kGranRows   = 64;                          // N rows per granule (one accumulator quarter)
-constexpr int kGranPlane  = kGranRows * 128;             // 8192 B: [64 rows][64 K] bf16, SW128 K-major
+constexpr int kGranRows   = 128;                         // N rows per granule (one accumulator half)
+constexpr int kGranPlane  = kGranRows * 128;             // 16384 B: [128 rows][64 K] bf16, SW128 K-major
 constexpr int kGranBytes  = 2 * kGranPlane;              // hi + lo
 constexpr int kOutPlane   = kOutPad * 128;               // 2048 B
 constexpr int kOutGranBytes = 2 * kOutPlane;
 __host__ __device__ constexpr int g_nkc(int g) { return g == 0 ? 1 : (g == 5 ? 5 : 4); }
-__host__ __device__ constexpr int g_layer_bytes(int g) { return g == 8 ? 4 * kOutGranBytes : 4 * g_nkc(g) * kGranBytes; }
+__host__ __device__ constexpr int g_layer_bytes(int g) { return g == 8 ? 4 * kOutGranBytes : 2 * g_nkc(g) * kGranBytes; }
 __host__ __device__ constexpr int g_layer_off(int g) {
   int o = 0;
   for (int i = 0; i < g; ++i) o += g_layer_bytes(i);
   return o;
 }
 constexpr int kTcwBytes = g_layer_off(kNumG);            // 1 982 464 B per tile pass
-constexpr int kGranPerTile = 4 * (1 + 4 * 4 + 5 + 2 * 4) + 4;   // 124
+constexpr int kGranPerTile = 2 * (1 + 4 * 4 + 5 + 2 * 4) + 4;   // 64 granules = 128 planes
 
 struct Layout {
   size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, total;

@@ -17,7 +17,9 @@
 //                 bf16 hi/lo split -> tcgen05.st over the same columns), so the next layer's MMAs over
 //                 K-chunk q start as soon as quarter q is converted while later quarters still compute.
 //   weights     : streamed from L2 (blob TCW section, pre-swizzled smem images) by 1-D bulk copies
-//                 into a 9-stage ring of 16 KB granules (64 N-rows x 64 K, hi plane + lo plane).
+//                 into a 9-stage ring of 16 KB planes (128 N-rows x 64 K, bf16; a granule = hi plane
+//                 then lo plane).  MMAs are M=128 x N=128 (one accumulator half) so that the single
+//                 issuing thread needs one instruction per 64 tensor-pipe cycles.
 //   PE          : computed by 4 dedicated warps one tile ahead, written as a K-major SW128 bf16 hi/lo
 //                 A-operand image in shared memory (used by G0 and again by G5).
 //
@@ -40,7 +42,8 @@ constexpr int PE_PLANE = TC_TM * 128;              // 16 KB: [128 rows][64 K] bf
 constexpr int PE_BUF = 2 * PE_PLANE;               // hi + lo
 constexpr int SM_PE = 0;                           // 2 buffers
 constexpr int SM_STG = SM_PE + 2 * PE_BUF;         // 65536
-constexpr int SM_TCBIAS = SM_STG + NSTG * kGranBytes;
+constexpr int kStageBytes = kGranPlane;            // one plane per ring stage
+constexpr int SM_TCBIAS = SM_STG + NSTG * kStageBytes;
 constexpr int SM_FBIAS = SM_TCBIAS + kNumG * 256 * 4;
 constexpr int SM_BAR = SM_FBIAS + 2 * 2 * 256 * 4;
 constexpr int NBAR = 2 * NSTG + 2 + 2 + 4 + 4;
@@ -128,10 +131,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 
 // Bounded mbarrier wait: a protocol bug must surface as a trapped kernel, never as a hung GPU box.
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (BACKOFF) __nanosleep(128);     // roles that run ahead (producers) must not steal issue slots while they wait
     if (clock64() - t0 > 4000000000ll) {
       printf("s2l tc kernel: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
              threadIdx.x, parity);
@@ -195,23 +200,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   if (warp == 0) {
     // =============================================================== weight producer
     if (elect_one()) {
-      long long c = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
         for (int g = 0; g < kNumG; ++g) {
-          const int ngran = (g == 8) ? 4 : 4 * g_nkc(g);
-          const int plane = (g == 8) ? kOutPlane : kGranPlane;
+          const int ngran = (g == 8) ? 4 : 2 * g_nkc(g);
+          const uint32_t plane = (g == 8) ? kOutPlane : kGranPlane;
           const uint8_t* src = tcw + g_layer_off(g);
-          for (int gi = 0; gi < ngran; ++gi, ++c) {
-            const int stage = (int)(c % NSTG);
-            mbar_wait_wd(&b_empty[stage], (uint32_t)(((c / NSTG) & 1) ^ 1), 100 + stage);
-            uint8_t* dst = smem + SM_STG + stage * kGranBytes;
-            if (NPASS == 3) {
-              mbar_arrive_expect_tx(&b_full[stage], 2 * plane);
-              bulk_g2s(dst, src + (size_t)gi * 2 * plane, 2 * plane, &b_full[stage]);
-            } else {
-              mbar_arrive_expect_tx(&b_full[stage], plane);
-              bulk_g2s(dst, src + (size_t)gi * 2 * plane, plane, &b_full[stage]);
-            }
+#pragma unroll 1
+          for (int pi = 0; pi < ngran * 2; ++pi) {           // planes in issue order: hi(gi), lo(gi), hi(gi+1), ...
+            if (NPASS == 1 && (pi & 1)) continue;
+            mbar_wait_wd<true>(&b_empty[stage], phase ^ 1u, 100 + stage);
+            mbar_arrive_expect_tx(&b_full[stage], plane);
+            bulk_g2s(smem + SM_STG + stage * kStageBytes, src + (size_t)pi * plane, plane, &b_full[stage]);
+            if (++stage == NSTG) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -219,62 +222,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   } else if (warp == 1) {
     // =============================================================== MMA issuer (one thread)
     if (elect_one()) {
-      long long c = 0;
-      uint32_t epi_par[4] = {0, 0, 0, 0};
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t epi_par = 0;                       // bit hk = parity to wait for on epi_done[hk]
       int rp = 0;
       long long it = 0;
+      constexpr uint32_t kDescHi = 0x40004040u;   // SBO=64 | version=1 | SWIZZLE_128B  (upper descriptor word)
+      auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi << 32) | lo; };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = (int)(it & 1);
-        const uint32_t pe_hi = smem_u32(smem + SM_PE + buf * PE_BUF);
-        const uint32_t pe_lo = pe_hi + PE_PLANE;
+        const uint32_t pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
+        const uint32_t pe_lo = pe_hi + (PE_PLANE >> 4);
+#pragma unroll 1
         for (int g = 0; g < kNumG; ++g) {
           const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
           const uint32_t a_region = tmem_base + (rp ? 0u : 256u);
-          const int nq = (g == 8) ? 1 : 4;
-          const uint32_t idesc = (g == 8) ? idesc_bf16(kOutPad) : idesc_bf16(64);
-          const int plane = (g == 8) ? kOutPlane : kGranPlane;
+          const int nh = (g == 8) ? 1 : 2;
+          const uint32_t idesc = (g == 8) ? idesc_bf16(kOutPad) : idesc_bf16(kGranRows);
           const int nkc = g_nkc(g);
-          for (int q = 0; q < nq; ++q) {
-            const uint32_t d_addr = d_region + (uint32_t)q * 64u;
-            for (int kc = 0; kc < nkc; ++kc, ++c) {
+#pragma unroll 1
+          for (int h = 0; h < nh; ++h) {
+            const uint32_t d_addr = d_region + (uint32_t)h * 128u;
+#pragma unroll 1
+            for (int kc = 0; kc < nkc; ++kc) {
               const bool is_pe = (g == 0) || (g == 5 && kc == 0);
               const int hk = (g == 5) ? kc - 1 : kc;
-              if (q == 0) {
+              if (h == 0) {
                 if (g == 0) mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 200 + buf);
                 if (!is_pe) {
-                  mbar_wait_wd(&epi_done[hk], epi_par[hk], 300 + hk);
-                  epi_par[hk] ^= 1;
+                  mbar_wait_wd(&epi_done[hk], (epi_par >> hk) & 1u, 300 + hk);
+                  epi_par ^= 1u << hk;
                 }
               }
-              const int stage = (int)(c % NSTG);
-              mbar_wait_wd(&b_full[stage], (uint32_t)((c / NSTG) & 1), 400 + stage);
+              // A chunk layout in TMEM (64 cols): [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
+              const uint32_t a_t = a_region + (uint32_t)hk * 64u;
+              // ---- hi weight plane: A_hi*W_hi (+ A_lo*W_hi)
+              mbar_wait_wd(&b_full[stage], phase, 400 + stage);
               tc_fence_after();
-              const uint32_t b_hi = smem_u32(smem + SM_STG + stage * kGranBytes);
-              const uint32_t b_lo = b_hi + plane;
-#pragma unroll
-              for (int s = 0; s < 4; ++s) {
-                const uint32_t acc0 = (kc == 0 && s == 0) ? 0u : 1u;
-                const uint64_t bd_hi = sw128_desc(b_hi + s * 32);
+              {
+                const uint32_t b = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
                 if (is_pe) {
-                  const uint64_t ad_hi = sw128_desc(pe_hi + s * 32);
-                  umma_ss(d_addr, ad_hi, bd_hi, idesc, acc0);
-                  if (NPASS == 3) {
-                    umma_ss(d_addr, sw128_desc(pe_lo + s * 32), bd_hi, idesc, 1u);
-                    umma_ss(d_addr, ad_hi, sw128_desc(b_lo + s * 32), idesc, 1u);
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) {
+                    umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, (kc == 0 && s == 0) ? 0u : 1u);
+                    if (NPASS == 3) umma_ss(d_addr, mk(pe_lo + 2 * s), mk(b + 2 * s), idesc, 1u);
                   }
                 } else {
-                  // A chunk layout in TMEM (64 cols): [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
-                  const uint32_t a_hi = a_region + (uint32_t)hk * 64u + (uint32_t)(s >> 1) * 32u + (uint32_t)(s & 1) * 8u;
-                  umma_ts(d_addr, a_hi, bd_hi, idesc, acc0);
-                  if (NPASS == 3) {
-                    umma_ts(d_addr, a_hi + 16u, bd_hi, idesc, 1u);
-                    umma_ts(d_addr, a_hi, sw128_desc(b_lo + s * 32), idesc, 1u);
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) {
+                    const uint32_t a_hi = a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8);
+                    umma_ts(d_addr, a_hi, mk(b + 2 * s), idesc, (kc == 0 && s == 0) ? 0u : 1u);
+                    if (NPASS == 3) umma_ts(d_addr, a_hi + 16u, mk(b + 2 * s), idesc, 1u);
                   }
                 }
               }
               umma_commit(&b_empty[stage]);      // stage reusable once these MMAs retire
+              if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+              // ---- lo weight plane: A_hi*W_lo
+              if (NPASS == 3) {
+                mbar_wait_wd(&b_full[stage], phase, 450 + stage);
+                tc_fence_after();
+                const uint32_t b = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
+                if (is_pe) {
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, 1u);
+                } else {
+#pragma unroll
+                  for (int s = 0; s < 4; ++s)
+                    umma_ts(d_addr, a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8), mk(b + 2 * s), idesc, 1u);
+                }
+                umma_commit(&b_empty[stage]);
+                if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+              }
             }
-            umma_commit(&acc_full[q]);           // accumulator quarter q of layer g complete
+            umma_commit(&acc_full[h]);           // accumulator half h of layer g complete
           }
           if (g == 5) umma_commit(&pe_empty[buf]);   // last reader of this tile's PE image
           rp ^= 1;
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       const int buf = (int)(it & 1);
       const int f = (int)(tile / a.tiles_per_frame);
       const long long p = (tile % a.tiles_per_frame) * TC_TM + r;
-      mbar_wait_wd(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
+      mbar_wait_wd<true>(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
       float e[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) e[i] = 0.f;
@@ -351,9 +372,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
         const float* bias = (g == 0) ? (fbias_s + buf * 512) : (g == 5) ? (fbias_s + buf * 512 + 256) : (tcbias_s + g * 256);
         for (int q = 0; q < 4; ++q) {
-          mbar_wait_wd(&acc_full[q], acc_par[q], 700 + q);
-          acc_par[q] ^= 1;
-          tc_fence_after();
+          if ((q & 1) == 0) {                       // accumulators complete per 128-column half
+            mbar_wait_wd(&acc_full[q >> 1], acc_par[q >> 1], 700 + q);
+            acc_par[q >> 1] ^= 1;
+            tc_fence_after();
+          }
           const uint32_t taddr = d_region + lane_sel + (uint32_t)(q * 64 + half * 32);
           uint32_t v[32];
           tmem_ld32(taddr, v);

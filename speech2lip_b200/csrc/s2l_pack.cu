@@ -110,12 +110,12 @@ __global__ void pack_tcw_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch
   uint8_t* T = blob + L.off_tcw;
   // one thread per (granule, row, k) element; granule index space = sum over layers
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // decode: layers 0..7 have 4*nkc granules of 64x64; layer 8 has 4 granules of 16x64
+  // decode: layers 0..7 have 2*nkc granules of 128x64 (half h, K-chunk kc); layer 8 has 4 granules of 16x64
   long long rem = gid;
-  int g = 0, rows = 64;
+  int g = 0, rows = kGranRows;
   for (; g < kNumG; ++g) {
-    rows = (g == 8) ? kOutPad : 64;
-    const long long cnt = (long long)((g == 8) ? 4 : 4 * g_nkc(g)) * rows * 64;
+    rows = (g == 8) ? kOutPad : kGranRows;
+    const long long cnt = (long long)((g == 8) ? 4 : 2 * g_nkc(g)) * rows * 64;
     if (rem < cnt) break;
     rem -= cnt;
   }
@@ -125,9 +125,9 @@ __global__ void pack_tcw_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch
   const int r = (int)(rem % per_gran);
   const int n = r / 64, k = r % 64;
   const int nkc = g_nkc(g);
-  const int q = (g == 8) ? 0 : gi / nkc;
+  const int h = (g == 8) ? 0 : gi / nkc;
   const int kc = (g == 8) ? gi : gi % nkc;
-  const int ng = q * 64 + n;
+  const int ng = h * kGranRows + n;
   float v;
   if (g == 0) {
     v = C[C_FOLD0 + ng * 64 + k];
