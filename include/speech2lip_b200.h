@@ -147,6 +147,19 @@ int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, const float* au
                           float* rgb, float* weights, float* depth, void* scratch, int32_t precision,
                           void* stream);
 
+/* Replaces: the pre-UNet part of TalkingFace.post_fusion2_onlylip_light (tf_nerf.py:334-386, inference branch,
+ * no black-hole augmentation): paste lip crop -> blend with canonical lip mask -> grid_sample canonical->observed
+ * with `coord` -> binarise warped mask -> blend with rgb_gt.  Layouts: rgb_lip [B,lh,lw,3], face_canonical [B,h,w,3],
+ * rgb_gt [B,Hf,Wf,3], mask_lip_canonical [B,h,w,3], coord [B,Hf,Wf,2] in [-1,1].
+ *   paste_shift = 1 for datasets whose path contains 'may'/'macron'/'obama_adnerf'/'obama2_face_crop' (tf_nerf.py:345-348)
+ *   expand_pad  = lip_w/5 (or lip_w/12) when cfg expand_lip_mask, -1 to warp the lip mask itself (tf_nerf.py:354-363)
+ * Outputs: fused_nchw [B,3,Hf,Wf] (the UNet input), merged_canonical [B,h,w,3] (may be NULL). */
+int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* face_canonical, const float* rgb_gt,
+                                const float* mask_lip_canonical, const float* coord, int32_t batch, int32_t lip_h,
+                                int32_t lip_w, int32_t face_h, int32_t face_w, int32_t out_h, int32_t out_w,
+                                int32_t lefttop_x, int32_t lefttop_y, int32_t paste_shift, int32_t expand_pad,
+                                float* fused_nchw, float* merged_canonical, void* stream);
+
 /* Number of kernels of this library launched by this thread since the last reset (bench "gpu_launches"). */
 int64_t s2l_launch_count(int32_t reset);
 

@@ -217,6 +217,36 @@ def render_volumetric(sd, audio, index, H, W, S, focal, c2w, near=0.0, far=1.0, 
     return rgb.reshape(H, W, 3)
 
 
+def post_fusion_compose(rgb_lip, rgb_face_canonical, rgb_gt, mask_lip_canonical, lip_lefttop_x, lip_lefttop_y, coord,
+                        data_path="dataset/may_face_crop_lip", expand_lip_mask=True):
+    """Pre-UNet part of TalkingFace.post_fusion2_onlylip_light, tf_nerf.py:334-386 (inference branch: no
+    black-hole augmentation).  Returns (rgb_merged_new [B,H,W,3], rgb_merged_canonical [B,h,w,3])."""
+    h, w = rgb_face_canonical.shape[1:3]
+    lip_h, lip_w = rgb_lip.shape[1:3]
+    left = lip_lefttop_x - 1
+    right = w - (left + lip_w)
+    up = lip_lefttop_y - 1
+    down = h - (up + lip_h)
+    if any(k in data_path for k in ("macron", "obama_adnerf", "obama2_face_crop", "may")):      # :345-348
+        pad = (left + 1, right - 1, up + 1, down - 1)
+    else:
+        pad = (left, right, up, down)
+    lip_pad = F.pad(rgb_lip.permute(0, 3, 1, 2), pad=pad, mode="constant", value=0).permute(0, 2, 3, 1)
+    canon = mask_lip_canonical * lip_pad + (1 - mask_lip_canonical) * rgb_face_canonical            # :352
+    mask = mask_lip_canonical
+    if expand_lip_mask:                                                                             # :354-363
+        p = lip_w // 12 if "obama2_face_crop" in data_path else lip_w // 5
+        tmp = torch.zeros_like(mask_lip_canonical)
+        tmp[:, lip_lefttop_y - p:lip_lefttop_y + lip_h + 2 * p, lip_lefttop_x - p:lip_lefttop_x + lip_w + p, :] = 1
+        mask = torch.ones_like(mask_lip_canonical) * tmp
+    merged = F.grid_sample(canon.permute(0, 3, 1, 2), coord, align_corners=False)                   # :365
+    m = F.grid_sample(mask.float().permute(0, 3, 1, 2), coord, align_corners=False)
+    m[m != 0] = 1
+    m = m.int()
+    out = m * merged + (1 - m) * rgb_gt.permute(0, 3, 1, 2)                                          # :386
+    return out.permute(0, 2, 3, 1), canon
+
+
 def psnr(a, b, peak=1.0):
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     if mse == 0:

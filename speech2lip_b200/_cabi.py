@@ -52,6 +52,7 @@ SYMBOLS = {
     "s2l_render_scratch_bytes": (C.c_size_t, [C.POINTER(S2LGeom)]),
     "s2l_render_frames": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "s2l_post_fusion_compose": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p] * 3),
     "s2l_launch_count": (C.c_int64, [C.c_int32]),
 }
 

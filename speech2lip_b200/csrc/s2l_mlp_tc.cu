@@ -371,38 +371,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       for (int g = 0; g < 8; ++g) {
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
         const float* bias = (g == 0) ? (fbias_s + buf * 512) : (g == 5) ? (fbias_s + buf * 512 + 256) : (tcbias_s + g * 256);
-        for (int q = 0; q < 4; ++q) {
-          if ((q & 1) == 0) {                       // accumulators complete per 128-column half
-            mbar_wait_wd(&acc_full[q >> 1], acc_par[q >> 1], 700 + q);
-            acc_par[q >> 1] ^= 1;
-            tc_fence_after();
-          }
-          const uint32_t taddr = d_region + lane_sel + (uint32_t)(q * 64 + half * 32);
-          uint32_t v[32];
-          tmem_ld32(taddr, v);
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {               // accumulators complete per 128-column half
+          mbar_wait_wd(&acc_full[hh], acc_par[hh], 700 + hh);
+          acc_par[hh] ^= 1;
+          tc_fence_after();
+          // both quarters of the half are loaded up front so the second load's latency hides behind the
+          // first quarter's conversion; each quarter is released to the MMA thread as soon as it is stored
+          const uint32_t taddr0 = d_region + lane_sel + (uint32_t)(hh * 128 + half * 32);
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr0, va);
+          tmem_ld32(taddr0 + 64u, vb);
           tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + half * 32);
-          uint32_t o[32];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bb = b4[j4];
-            const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
-            const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
-            const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
-            const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
-            const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
-            o[2 * j4] = h0;
-            o[2 * j4 + 1] = h1;
-            if (NPASS == 3) {
-              o[16 + 2 * j4] = pack_bf16x2(x0 - __uint_as_float(h0 << 16), x1 - __uint_as_float(h0 & 0xffff0000u));
-              o[16 + 2 * j4 + 1] = pack_bf16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u));
+          for (int qq = 0; qq < 2; ++qq) {
+            const int q = hh * 2 + qq;
+            const uint32_t taddr = taddr0 + (uint32_t)(qq * 64);
+            const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + half * 32);
+            uint32_t o[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bb = b4[j4];
+              const uint32_t* v = qq ? vb : va;
+              const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
+              const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+              const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
+              const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+              const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
+              o[2 * j4] = h0;
+              o[2 * j4 + 1] = h1;
+              if (NPASS == 3) {
+                o[16 + 2 * j4] = pack_bf16x2(x0 - __uint_as_float(h0 << 16), x1 - __uint_as_float(h0 & 0xffff0000u));
+                o[16 + 2 * j4 + 1] = pack_bf16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u));
+              }
             }
+            if (NPASS == 3) tmem_st32(taddr, o);
+            else tmem_st16(taddr, o);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&epi_done[q]);
           }
-          if (NPASS == 3) tmem_st32(taddr, o);
-          else tmem_st16(taddr, o);
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&epi_done[q]);
         }
         if (g == 5) mbar_arrive(&pe_empty[buf]);      // this thread no longer reads fbias_s[buf]
         rp ^= 1;

@@ -1,0 +1,151 @@
+// Post-fusion compose + warp (SURVEY §8(f) "next" rank 1): the pre-UNet part of
+// TalkingFace.post_fusion2_onlylip_light (tf_nerf.py:334-386, inference branch) as ONE gather-blend kernel:
+//   paste the rendered lip crop into the canonical face (F.pad), blend with the canonical lip mask,
+//   warp canonical -> observed with the per-frame `coord` grid (2x F.grid_sample, bilinear, zeros,
+//   align_corners=False), binarise the warped mask, blend with the ground-truth frame.
+// HBM-bound: per output pixel 8 B coord + 12 B gt read + 12 B written, plus 4-tap gathers of the
+// canonical face / mask that hit L1/L2 (neighbouring pixels sample neighbouring texels); the eager
+// reference materialises ~10 full-size intermediates.  One thread per observed pixel, coalesced
+// float2 / scalar accesses, output written planar (NCHW) because the UNet consumes NCHW.
+#include "s2l_common.cuh"
+
+namespace s2l {
+
+struct PfArgs {
+  const float* lip;      // [B,lh,lw,3]
+  const float* face;     // [B,h,w,3]   canonical face
+  const float* gt;       // [B,Hf,Wf,3] observed ground truth
+  const float* mask;     // [B,h,w,3]   canonical lip mask
+  const float* coord;    // [B,Hf,Wf,2] sampling grid in [-1,1]
+  float* fused;          // [B,3,Hf,Wf]
+  int B, lh, lw, h, w, Hf, Wf;
+  int px0, py0;          // canonical position of lip pixel (0,0)
+  int rect;              // 1: warp the expanded rectangle mask, 0: warp the lip mask itself
+  int ry0, ry1, rx0, rx1;
+};
+
+// merged_canonical[b,cy,cx,c] = m*lip_pad + (1-m)*face      (tf_nerf.py:352)
+__device__ __forceinline__ float merged_canon(const PfArgs& a, int b, int cy, int cx, int c) {
+  const size_t idx = (((size_t)b * a.h + cy) * a.w + cx) * 3 + c;
+  const float m = a.mask[idx];
+  const int ly = cy - a.py0, lx = cx - a.px0;
+  float lipv = 0.f;
+  if (ly >= 0 && ly < a.lh && lx >= 0 && lx < a.lw) lipv = a.lip[(((size_t)b * a.lh + ly) * a.lw + lx) * 3 + c];
+  return __fadd_rn(__fmul_rn(m, lipv), __fmul_rn(__fsub_rn(1.f, m), a.face[idx]));
+}
+
+__global__ void __launch_bounds__(256) post_fusion_kernel(PfArgs a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)a.Hf * a.Wf;
+  if (gid >= npix * a.B) return;
+  const int b = (int)(gid / npix);
+  const long long pix = gid % npix;
+  const float2 g = reinterpret_cast<const float2*>(a.coord)[gid];
+  // grid_sampler_unnormalize, align_corners=False: ((coord + 1) * size - 1) / 2
+  const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.x, 1.f), (float)a.w), 1.f), 0.5f);
+  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.y, 1.f), (float)a.h), 1.f), 0.5f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = __fsub_rn(ix, fx), wy1 = __fsub_rn(iy, fy);
+  const float wx0 = __fsub_rn((float)x1, ix), wy0 = __fsub_rn((float)y1, iy);
+  const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+  const bool inx0 = x0 >= 0 && x0 < a.w, inx1 = x1 >= 0 && x1 < a.w, iny0 = y0 >= 0 && y0 < a.h, iny1 = y1 >= 0 && y1 < a.h;
+  // ---- issue every load of the pixel up front (4 taps x {mask, face, lip} x 3 channels + gt): the kernel is
+  //      latency-bound otherwise (coord -> address -> gather is a dependent chain)
+  const int tx[4] = {x0, x1, x0, x1}, ty[4] = {y0, y0, y1, y1};
+  const bool tin[4] = {iny0 && inx0, iny0 && inx1, iny1 && inx0, iny1 && inx1};
+  const float tw[4] = {wnw, wne, wsw, wse};          // accumulation order nw, ne, sw, se as in ATen's grid_sampler_2d
+  float mk[4][3], fc[4][3], lp[4][3];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { mk[t][c] = 0.f; fc[t][c] = 0.f; lp[t][c] = 0.f; }
+    if (tin[t]) {
+      const size_t idx = (((size_t)b * a.h + ty[t]) * a.w + tx[t]) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { mk[t][c] = __ldg(a.mask + idx + c); fc[t][c] = __ldg(a.face + idx + c); }
+      const int ly = ty[t] - a.py0, lx = tx[t] - a.px0;
+      if (ly >= 0 && ly < a.lh && lx >= 0 && lx < a.lw) {
+        const size_t li = (((size_t)b * a.lh + ly) * a.lw + lx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lp[t][c] = __ldg(a.lip + li + c);
+      }
+    }
+  }
+  float gtv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gtv[c] = __ldg(a.gt + gid * 3 + c);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float acc = 0.f, macc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (tin[t]) {
+        // merged_canonical = m*lip_pad + (1-m)*face   (tf_nerf.py:352), then the bilinear tap
+        const float mc = __fadd_rn(__fmul_rn(mk[t][c], lp[t][c]), __fmul_rn(__fsub_rn(1.f, mk[t][c]), fc[t][c]));
+        acc = __fadd_rn(acc, __fmul_rn(mc, tw[t]));
+        const float mv = a.rect ? ((ty[t] >= a.ry0 && ty[t] < a.ry1 && tx[t] >= a.rx0 && tx[t] < a.rx1) ? 1.f : 0.f) : mk[t][c];
+        macc = __fadd_rn(macc, __fmul_rn(mv, tw[t]));
+      }
+    }
+    // mask[mask != 0] = 1 ; out = mask*merged + (1-mask)*gt      (tf_nerf.py:367-386)
+    a.fused[((size_t)b * 3 + c) * npix + pix] = (macc != 0.f) ? acc : gtv[c];
+  }
+}
+
+__global__ void merged_canonical_kernel(PfArgs a, float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)a.B * a.h * a.w * 3;
+  if (gid >= n) return;
+  const int c = (int)(gid % 3);
+  const long long p = gid / 3;
+  const int cx = (int)(p % a.w), cy = (int)((p / a.w) % a.h), b = (int)(p / ((long long)a.w * a.h));
+  out[gid] = merged_canon(a, b, cy, cx, c);
+}
+
+}  // namespace s2l
+
+using namespace s2l;
+
+extern "C" int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* face_canonical, const float* rgb_gt,
+                                           const float* mask_lip_canonical, const float* coord, int32_t batch, int32_t lip_h,
+                                           int32_t lip_w, int32_t face_h, int32_t face_w, int32_t out_h, int32_t out_w,
+                                           int32_t lefttop_x, int32_t lefttop_y, int32_t paste_shift, int32_t expand_pad,
+                                           float* fused_nchw, float* merged_canonical, void* stream) {
+  if (!rgb_lip || !face_canonical || !rgb_gt || !mask_lip_canonical || !coord || !fused_nchw) {
+    set_error("s2l_post_fusion_compose: null argument");
+    return 1;
+  }
+  if (batch < 0 || lip_h <= 0 || lip_w <= 0 || face_h <= 0 || face_w <= 0 || out_h <= 0 || out_w <= 0) {
+    set_error("s2l_post_fusion_compose: bad sizes");
+    return 2;
+  }
+  PfArgs a{};
+  a.lip = rgb_lip; a.face = face_canonical; a.gt = rgb_gt; a.mask = mask_lip_canonical; a.coord = coord; a.fused = fused_nchw;
+  a.B = batch; a.lh = lip_h; a.lw = lip_w; a.h = face_h; a.w = face_w; a.Hf = out_h; a.Wf = out_w;
+  // F.pad(left+1, ..., up+1, ...) with left = x-1, up = y-1 for the 'may'-style datasets, else (left, up)  (tf_nerf.py:345-350)
+  a.px0 = paste_shift ? lefttop_x : lefttop_x - 1;
+  a.py0 = paste_shift ? lefttop_y : lefttop_y - 1;
+  if (a.px0 < 0 || a.py0 < 0 || a.px0 + lip_w > face_w || a.py0 + lip_h > face_h) {
+    set_error("s2l_post_fusion_compose: lip crop (%dx%d at %d,%d) does not fit the %dx%d canonical face", lip_w, lip_h, a.px0, a.py0, face_w, face_h);
+    return 2;
+  }
+  a.rect = expand_pad >= 0;
+  if (a.rect) {
+    // mask[:, y-p : y+lh+2p, x-p : x+lw+p] = 1                  (tf_nerf.py:362)
+    if (lefttop_y - expand_pad < 0 || lefttop_x - expand_pad < 0) { set_error("s2l_post_fusion_compose: expanded mask starts outside the image"); return 2; }
+    a.ry0 = lefttop_y - expand_pad; a.ry1 = min(face_h, lefttop_y + lip_h + 2 * expand_pad);
+    a.rx0 = lefttop_x - expand_pad; a.rx1 = min(face_w, lefttop_x + lip_w + expand_pad);
+  }
+  if (batch == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = (long long)batch * out_h * out_w;
+  post_fusion_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+  if (!check_launch("post_fusion_kernel")) return 5;
+  if (merged_canonical) {
+    const long long m = (long long)batch * face_h * face_w * 3;
+    merged_canonical_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a, merged_canonical);
+    if (!check_launch("merged_canonical_kernel")) return 5;
+  }
+  return 0;
+}

@@ -159,6 +159,31 @@ def get_rays(H, W, focal, c2w):
     return ro, rd
 
 
+def post_fusion_compose(rgb_lip, face_canonical, rgb_gt, mask_lip_canonical, coord, lefttop_x, lefttop_y,
+                        paste_shift=True, expand_pad=-1, want_canonical=True):
+    """Pre-UNet part of post_fusion2_onlylip_light (tf_nerf.py:334-386, inference branch) as one kernel.
+    Returns (fused [B,3,Hf,Wf] NCHW — the UNet input, merged_canonical [B,h,w,3] or None)."""
+    lib = _cabi.lib()
+    lip, face, gt = _f32c(rgb_lip, "rgb_lip"), _f32c(face_canonical, "rgb_face_canonical"), _f32c(rgb_gt, "rgb_gt")
+    mask, coord = _f32c(mask_lip_canonical, "mask_lip_canonical"), _f32c(coord, "coord")
+    B, lh, lw = lip.shape[0], lip.shape[1], lip.shape[2]
+    h, w = face.shape[1], face.shape[2]
+    Hf, Wf = coord.shape[1], coord.shape[2]
+    if mask.shape[-1] == 1:
+        mask = mask.expand(-1, -1, -1, 3).contiguous()
+    if tuple(mask.shape) != (B, h, w, 3) or tuple(gt.shape) != (B, Hf, Wf, 3) or tuple(face.shape) != (B, h, w, 3) \
+            or tuple(coord.shape) != (B, Hf, Wf, 2) or lip.shape[-1] != 3:
+        raise ValueError("post_fusion_compose: inconsistent shapes lip %s face %s gt %s mask %s coord %s" % (
+            tuple(lip.shape), tuple(face.shape), tuple(gt.shape), tuple(mask.shape), tuple(coord.shape)))
+    fused = torch.empty(B, 3, Hf, Wf, device=lip.device)
+    canon = torch.empty(B, h, w, 3, device=lip.device) if want_canonical else None
+    with torch.cuda.device(lip.device):
+        _cabi.check(lib.s2l_post_fusion_compose(_ptr(lip), _ptr(face), _ptr(gt), _ptr(mask), _ptr(coord), B, lh, lw, h, w, Hf, Wf,
+                                                int(lefttop_x), int(lefttop_y), 1 if paste_shift else 0, int(expand_pad),
+                                                _ptr(fused), _ptr(canon), _stream()), "s2l_post_fusion_compose")
+    return fused, canon
+
+
 class LipRenderer:
     """Batched frame renderer over one PackedWeights blob.
 

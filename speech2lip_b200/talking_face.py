@@ -220,13 +220,24 @@ class TalkingFace(nn.Module):
         observed with `coord`, optional black-hole augmentation, UNet refine.  [B,H,W,C] layouts."""
         if not self.use_light_unet:
             return None
+        shifted_ds = any(s in self.data_path for s in ('macron', 'obama_adnerf', 'obama2_face_crop', 'may'))
+        aug = use_post_fusion_blackaug and random.random() > 0.5        # same RNG draw as tf_nerf.py:369
+        if rgb_lip_warped.is_cuda and not aug:
+            # fused gather-blend kernel (SURVEY 8(f) rank 1); the UNet stays cuDNN
+            lw_ = rgb_lip_warped.shape[2]
+            pad_ = -1
+            if self.expand_lip_mask:
+                pad_ = lw_ // 12 if 'obama2_face_crop' in self.data_path else lw_ // 5
+            fused, canon = R.post_fusion_compose(rgb_lip_warped, rgb_face_canonical, rgb_gt, mask_lip_canonical, coord,
+                                                 int(lip_lefttop_x), int(lip_lefttop_y), shifted_ds, pad_)
+            recon = self.post_fusion_unet(fused)
+            return recon.permute(0, 2, 3, 1), fused.permute(0, 2, 3, 1), canon
         h, w = rgb_face_canonical.shape[1:3]
         lh, lw = rgb_lip_warped.shape[1:3]
         x0, y0 = int(lip_lefttop_x), int(lip_lefttop_y)
         left, up = x0 - 1, y0 - 1
         right, down = w - (left + lw), h - (up + lh)
-        shifted = any(s in self.data_path for s in ('macron', 'obama_adnerf', 'obama2_face_crop', 'may'))
-        pad = (left + 1, right - 1, up + 1, down - 1) if shifted else (left, right, up, down)
+        pad = (left + 1, right - 1, up + 1, down - 1) if shifted_ds else (left, right, up, down)
         lip_full = F.pad(rgb_lip_warped.permute(0, 3, 1, 2), pad=pad, mode='constant', value=0).permute(0, 2, 3, 1)
         merged_canonical = mask_lip_canonical * lip_full + (1 - mask_lip_canonical) * rgb_face_canonical
         mask = mask_lip_canonical
@@ -238,7 +249,7 @@ class TalkingFace(nn.Module):
         mask_obs = F.grid_sample(mask.float().permute(0, 3, 1, 2), coord, align_corners=False)
         mask_obs = (mask_obs != 0).int()
         gt = rgb_gt.permute(0, 3, 1, 2)
-        if use_post_fusion_blackaug and random.random() > 0.5:
+        if aug:
             face_obs = F.grid_sample((rgb_face_canonical > 0).float().permute(0, 3, 1, 2), coord, align_corners=False)
             face_obs = (face_obs == 1).float()
 

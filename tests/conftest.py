@@ -17,9 +17,10 @@ def pytest_configure(config):
 def golden():
     """tests/golden/reference_golden.npz -> {case: {key: ndarray}} (outputs of the REAL
     reference, produced by tests/golden/make_golden.py in the build container)."""
-    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
     cases = {}
-    for k in z.files:
-        c, name = k.split("/", 1)
-        cases.setdefault(c, {})[name] = z[k]
+    for fn in ("reference_golden.npz", "reference_golden_postfusion.npz"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", fn))
+        for k in z.files:
+            c, name = k.split("/", 1)
+            cases.setdefault(c, {})[name] = z[k]
     return cases

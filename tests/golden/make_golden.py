@@ -137,5 +137,34 @@ def main():
         print("  ", c)
 
 
+def main_postfusion():
+    """tests/golden/reference_golden_postfusion.npz: the reference's post_fusion2_onlylip (tf_nerf.py:287-389,
+    inference branch) on random images, a random lip mask and a smooth random warp; stores the two pre-UNet outputs."""
+    ns = load_reference()
+    torch.manual_seed(3)
+    m = ns.TalkingFace(device=torch.device("cpu"), cfg=ns.cfg, mode="eval").eval()
+    g = torch.Generator().manual_seed(42)
+    cases = {}
+    for name, (h, w, lh, lw, x0, y0) in {"pf_a": (40, 40, 8, 12, 14, 16), "pf_b": (36, 52, 6, 10, 20, 12)}.items():
+        B = 2
+        lip = torch.rand(B, lh, lw, 3, generator=g)
+        face = torch.rand(B, h, w, 3, generator=g)
+        gt = torch.rand(B, h, w, 3, generator=g)
+        face[:, :3] = 0
+        mask = torch.zeros(B, h, w, 3)
+        mask[:, y0 + 1:y0 + lh - 1, x0 + 1:x0 + lw - 2, :] = 1
+        mask[:, y0 + 2, x0 + 3, 1] = 0
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+        coord = torch.stack([xs, ys], -1)[None].repeat(B, 1, 1, 1)
+        coord = coord * 1.08 + 0.05 * torch.randn(B, h, w, 2, generator=g) * 0.3 + 0.03
+        with torch.no_grad():
+            recon, fused, canon = m.post_fusion2_onlylip(lip, face, gt, mask, x0, y0, coord, use_canonical_space=True)
+        cases[name] = dict(lip=lip.numpy(), face=face.numpy(), gt=gt.numpy(), mask=mask.numpy(), coord=coord.numpy(),
+                           x0=np.int64(x0), y0=np.int64(y0), fused=fused.numpy(), canon=canon.numpy())
+    flat = {"%s/%s" % (c, k): np.asarray(v) for c, d in cases.items() for k, v in d.items()}
+    np.savez_compressed(os.path.join(OUT, "reference_golden_postfusion.npz"), **flat)
+
+
 if __name__ == "__main__":
     main()
+    main_postfusion()

@@ -342,3 +342,39 @@ def test_talking_face_drop_in(S, golden):
         m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()))        # grad mode: backward not built yet
     rgb = m.renderer("bf16x3").render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([5]), H, W)
     assert maxabs((rgb[0] - 1.0).cpu(), g["rgb"]) < PARITY_TOL
+
+
+# ------------------------------------------------------------------------------------------ next row: post-fusion compose
+@pytest.mark.parametrize("case", ["pf_a", "pf_b"])
+def test_post_fusion_compose_vs_golden(S, golden, case):
+    """fused paste + mask + 2x grid_sample + blend kernel vs the REAL reference's outputs."""
+    g = golden[case]
+    t = lambda k: torch.from_numpy(g[k]).to(dev())
+    fused, canon = S.post_fusion_compose(t("lip"), t("face"), t("gt"), t("mask"), t("coord"), int(g["x0"]), int(g["y0"]),
+                                         paste_shift=True, expand_pad=g["lip"].shape[2] // 5)
+    assert maxabs(canon.cpu(), g["canon"]) == 0.0
+    err = maxabs(fused.permute(0, 2, 3, 1).cpu(), g["fused"])
+    print("post-fusion %s maxabs %.3e" % (case, err))
+    assert err < 2e-6
+    # unexpanded-mask variant against the oracle
+    f2, _ = S.post_fusion_compose(t("lip"), t("face"), t("gt"), t("mask"), t("coord"), int(g["x0"]), int(g["y0"]),
+                                  paste_shift=True, expand_pad=-1, want_canonical=False)
+    tc = lambda k: torch.from_numpy(g[k])
+    want, _ = O.post_fusion_compose(tc("lip"), tc("face"), tc("gt"), tc("mask"), int(g["x0"]), int(g["y0"]), tc("coord"),
+                                    expand_lip_mask=False)
+    assert maxabs(f2.permute(0, 2, 3, 1).cpu(), want) < 2e-6
+
+
+def test_talking_face_post_fusion_uses_kernel(S, golden):
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval").to(dev()).eval()
+    g = golden["pf_a"]
+    t = lambda k: torch.from_numpy(g[k]).to(dev())
+    from speech2lip_b200 import _cabi
+    _cabi.lib().s2l_launch_count(1)
+    with torch.no_grad():
+        recon, fused, canon = m.post_fusion2_onlylip(t("lip"), t("face"), t("gt"), t("mask"), int(g["x0"]), int(g["y0"]), t("coord"),
+                                                     use_canonical_space=True)
+    assert _cabi.lib().s2l_launch_count(0) == 2, "post-fusion did not go through the CUDA kernels"
+    assert recon.shape == fused.shape == (2, 40, 40, 3)
+    assert maxabs(fused.cpu(), g["fused"]) < 2e-6 and maxabs(canon.cpu(), g["canon"]) == 0.0

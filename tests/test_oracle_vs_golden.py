@@ -98,3 +98,23 @@ def test_fp64_truth_close_to_fp32_reference(golden):
     sd64 = O.to_torch_sd(synth.make_state_dict(0, "kaiming"), torch.float64)
     out = O.render_plain(sd64, torch.from_numpy(g["audio"]).double(), 5, 24, 32)
     assert np.abs(out.numpy() - g["rgb"]).max() < 2e-4
+
+
+@pytest.mark.parametrize("case", ["pf_a", "pf_b"])
+def test_post_fusion_compose(golden, case):
+    """the pre-UNet part of post_fusion2_onlylip_light (tf_nerf.py:334-386)."""
+    g = golden[case]
+    t = lambda k: torch.from_numpy(g[k])
+    fused, canon = O.post_fusion_compose(t("lip"), t("face"), t("gt"), t("mask"), int(g["x0"]), int(g["y0"]), t("coord"))
+    np.testing.assert_array_equal(canon.numpy(), g["canon"])
+    np.testing.assert_allclose(fused.numpy(), g["fused"], atol=1e-7, rtol=0)
+    # the drop-in module's PyTorch (CPU) branch must agree too
+    import json, os
+    from speech2lip_b200 import TalkingFace
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = json.load(open(os.path.join(root, "tests", "golden", "may_cfg.json")))
+    m = TalkingFace(device=torch.device("cpu"), cfg=cfg, mode="eval").eval()
+    with torch.no_grad():
+        _, fused2, canon2 = m.post_fusion2_onlylip(t("lip"), t("face"), t("gt"), t("mask"), int(g["x0"]), int(g["y0"]), t("coord"))
+    np.testing.assert_allclose(fused2.numpy(), g["fused"], atol=1e-7, rtol=0)
+    np.testing.assert_array_equal(canon2.numpy(), g["canon"])
