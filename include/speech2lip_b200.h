@@ -122,6 +122,21 @@ int32_t s2l_mlp_fwd(const void* blob, const S2LGeom* geom, const float* frame_bi
 int32_t s2l_rgb_forward_rows(const void* blob, const float* x, int64_t n_rows, int64_t time_idx,
                              int32_t has_time, float* out, int32_t uv_dims, int32_t out_ch, void* stream);
 
+/* Training forward of the general contract: same as s2l_rgb_forward_rows, and additionally saves the 10 activation
+ * tensors the backward needs: acts [10][N][256] = {net, h0..h4, h_skip, h5, h6, h7} (tf_nerf.py:252-281). */
+int32_t s2l_rgb_forward_rows_train(const void* blob, const float* x, int64_t n_rows, int64_t time_idx,
+                                   int32_t has_time, float* out, float* acts, int32_t uv_dims, int32_t out_ch,
+                                   void* stream);
+
+/* Replaces: autograd's backward through rgb_forward (loss.backward(), training.py:559), data-gradient half.
+ *   d_out [N,out_ch], acts from the training forward -> dsave [10][N][256] =
+ *   {d net, dPre0..dPre4, d h_skip, dPre5, dPre6, dPre7}.  Weight gradients are dPre_l^T * h_{l-1} (plain GEMMs). */
+int32_t s2l_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts, int64_t n_rows, float* dsave,
+                         int32_t out_ch, void* stream);
+
+/* Replaces: Embedder.__call__ (tf_nerf.py:404-425): x rows (first uv_dims floats of each row_stride-float row) -> pe [N,E]. */
+int32_t s2l_embed_fwd(const float* x, int64_t n_rows, int32_t row_stride, int32_t uv_dims, float* pe, void* stream);
+
 /* Replaces: the 4-tap blend of Trainer.predict_lip_image (training.py:238-249).
  *   raw [F*H*W*4, out_ch] (tap-minor) -> rgb [F,H,W,3] */
 int32_t s2l_ensemble4_blend(const float* raw, const S2LGeom* geom, float* rgb, void* stream);

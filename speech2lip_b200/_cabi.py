@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libs2l_b200.so")
+LIB_PATH = os.environ.get("S2L_LIB_PATH") or os.path.join(_HERE, "csrc", "libs2l_b200.so")   # env override: debug builds only
 
 NUM_PARAMS = 42
 PREC_FP32, PREC_BF16X3, PREC_BF16X1 = 0, 1, 2
@@ -45,6 +45,10 @@ SYMBOLS = {
                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "s2l_rgb_forward_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                          C.c_int32, C.c_int32, C.c_void_p]),
+    "s2l_rgb_forward_rows_train": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.c_int32, C.c_int32, C.c_void_p]),
+    "s2l_mlp_bwd_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "s2l_embed_fwd": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "s2l_ensemble4_blend": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p]),
     "s2l_composite_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

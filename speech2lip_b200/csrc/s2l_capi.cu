@@ -30,7 +30,10 @@ bool check_launch(const char* what) {
 int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out,
                     int out_ch, cudaStream_t st);
 int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, long long time_idx, int has_time,
-                         float* out, int uv_dims, int out_ch, cudaStream_t st);
+                         float* out, float* save, int uv_dims, int out_ch, cudaStream_t st);
+int launch_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts, long long n_rows, float* dsave,
+                        int out_ch, cudaStream_t st);
+int launch_embed(const float* x, long long n_rows, int row_stride, int uv_dims, float* pe, cudaStream_t st);
 int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
                   int npass, cudaStream_t st);
 
@@ -115,7 +118,29 @@ extern "C" int32_t s2l_rgb_forward_rows(const void* blob, const float* x, int64_
   if (!blob || (!x && n_rows > 0) || (!out && n_rows > 0)) { set_error("s2l_rgb_forward_rows: null argument"); return 1; }
   if (n_rows < 0) { set_error("s2l_rgb_forward_rows: negative n_rows"); return 2; }
   if ((uv_dims != 2 && uv_dims != 3) || out_ch < 1 || out_ch > 4) { set_error("s2l_rgb_forward_rows: unsupported dims uv_dims=%d out_ch=%d", uv_dims, out_ch); return 2; }
-  return launch_mlp_fp32_rows(blob, x, n_rows, time_idx, has_time, out, uv_dims, out_ch, reinterpret_cast<cudaStream_t>(stream));
+  return launch_mlp_fp32_rows(blob, x, n_rows, time_idx, has_time, out, nullptr, uv_dims, out_ch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t s2l_rgb_forward_rows_train(const void* blob, const float* x, int64_t n_rows, int64_t time_idx,
+                                              int32_t has_time, float* out, float* acts, int32_t uv_dims, int32_t out_ch,
+                                              void* stream) {
+  if (!blob || (n_rows > 0 && (!x || !out || !acts))) { set_error("s2l_rgb_forward_rows_train: null argument"); return 1; }
+  if (n_rows < 0) { set_error("s2l_rgb_forward_rows_train: negative n_rows"); return 2; }
+  if ((uv_dims != 2 && uv_dims != 3) || out_ch < 1 || out_ch > 4) { set_error("s2l_rgb_forward_rows_train: unsupported dims uv_dims=%d out_ch=%d", uv_dims, out_ch); return 2; }
+  return launch_mlp_fp32_rows(blob, x, n_rows, time_idx, has_time, out, acts, uv_dims, out_ch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t s2l_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts, int64_t n_rows, float* dsave,
+                                    int32_t out_ch, void* stream) {
+  if (!blob || (n_rows > 0 && (!d_out || !acts || !dsave))) { set_error("s2l_mlp_bwd_rows: null argument"); return 1; }
+  if (n_rows < 0 || out_ch < 1 || out_ch > 4) { set_error("s2l_mlp_bwd_rows: bad n_rows/out_ch"); return 2; }
+  return launch_mlp_bwd_rows(blob, d_out, acts, n_rows, dsave, out_ch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t s2l_embed_fwd(const float* x, int64_t n_rows, int32_t row_stride, int32_t uv_dims, float* pe, void* stream) {
+  if (n_rows > 0 && (!x || !pe)) { set_error("s2l_embed_fwd: null argument"); return 1; }
+  if (n_rows < 0 || (uv_dims != 2 && uv_dims != 3) || row_stride < uv_dims) { set_error("s2l_embed_fwd: bad arguments"); return 2; }
+  return launch_embed(x, n_rows, row_stride, uv_dims, pe, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t s2l_render_scratch_bytes(const S2LGeom* g) {

@@ -81,8 +81,14 @@ __host__ __device__ constexpr int g_layer_off(int g) {
 constexpr int kTcwBytes = g_layer_off(kNumG);            // 1 982 464 B per tile pass
 constexpr int kGranPerTile = 2 * (1 + 4 * 4 + 5 + 2 * 4) + 4;   // 64 granules = 128 planes
 
+// ---- DGRAD section (float offsets): untransposed [out][in=256] weights for the backward data-gradient GEMMs
+//      dX = dY * W.  Slots: pts_linears 0..4, pts_linears.5[:, :256], pts_linears.5[:, 256:], pts_linears 6, 7.
+constexpr int D_SLOTS = 9;
+__host__ __device__ constexpr int d_slot_off(int slot) { return slot * 65536; }
+constexpr int D_TOTAL = D_SLOTS * 65536;
+
 struct Layout {
-  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, total;
+  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, total;
 };
 __host__ __device__ inline Layout blob_layout() {
   Layout L;
@@ -93,6 +99,7 @@ __host__ __device__ inline Layout blob_layout() {
   L.off_fp32 = o;   o = al(o + sizeof(float) * F_TOTAL);
   L.off_tcbias = o; o = al(o + sizeof(float) * kNumG * 256);
   L.off_tcw = o;    o = al(o + kTcwBytes);
+  L.off_dgrad = o;  o = al(o + sizeof(float) * D_TOTAL);
   L.total = o;
   return L;
 }
@@ -130,6 +137,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
       : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~hint ns pass)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
   return done != 0;
 }

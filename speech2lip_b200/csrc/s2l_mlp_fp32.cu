@@ -6,101 +6,9 @@
 // Roles: this kernel is (a) the arithmetic reference on the GPU (true fp32), (b) the general
 // rgb_forward contract with an arbitrary latent per row (ROWLAT), where the audio term cannot be
 // hoisted into a per-frame bias.  The tensor-core kernel (s2l_mlp_tc.cu) is the throughput path.
-#include "s2l_common.cuh"
-#include "s2l_points.cuh"
+#include "s2l_fp32_core.cuh"
 
 namespace s2l {
-
-constexpr int TM = 64;        // points per tile
-constexpr int TMP = 68;       // padded row length of the [K][TM] activation buffers (bank spread, 16B aligned)
-constexpr int KC = 16;        // K rows per weight chunk
-constexpr int NS = 3;         // weight ring stages
-constexpr int CHUNK_FLOATS = KC * 256;
-constexpr int MAX_CHUNKS = 168;
-
-struct Fp32Program {
-  int n_chunks;                 // chunks per tile
-  int off[MAX_CHUNKS];          // float offset of each chunk from the blob base
-};
-
-struct Fp32Args {
-  const uint8_t* blob;
-  Layout L;
-  PointSrc src;
-  const float* frame_bias;      // [F,4,256] (non-ROWLAT)
-  const float* rows;            // ROWLAT: x [N, uv_dims+64]
-  long long time_idx;
-  int has_time;
-  float* out;                   // [F*P, out_ch]
-  int out_ch;
-  int n_frames;
-  long long tiles_per_frame;
-  Fp32Program prog;
-};
-
-struct Pipe {
-  long long c;        // chunks consumed so far by this CTA
-  long long total;    // chunks this CTA will consume in total
-};
-
-__device__ __forceinline__ void issue_chunk(const Fp32Args& a, float* wst, uint64_t* full, long long c) {
-  const int stage = (int)(c % NS);
-  const float* src = reinterpret_cast<const float*>(a.blob) + a.prog.off[c % a.prog.n_chunks];
-  mbar_arrive_expect_tx(&full[stage], CHUNK_FLOATS * 4);
-  bulk_g2s(wst + stage * CHUNK_FLOATS, src, CHUNK_FLOATS * 4, &full[stage]);
-}
-
-// acc[8 m][8 n] += A[k][m] * W[k][n] over `nchunks` 16-row weight chunks; A is [K][TMP] in smem.
-__device__ __forceinline__ void gemm_seg(float (&acc)[8][8], const float* Abuf, int nchunks, Pipe& ps,
-                                         const Fp32Args& a, float* wst, uint64_t* full, int m0, int tn) {
-  for (int j = 0; j < nchunks; ++j) {
-    const int stage = (int)(ps.c % NS);
-    mbar_wait(&full[stage], (uint32_t)((ps.c / NS) & 1));
-    const float* Wc = wst + stage * CHUNK_FLOATS;
-    const float* Ac = Abuf + (size_t)j * KC * TMP + m0;
-#pragma unroll 4
-    for (int kk = 0; kk < KC; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(Ac + kk * TMP);
-      const float4 a1 = *reinterpret_cast<const float4*>(Ac + kk * TMP + 4);
-      const float4 w0 = *reinterpret_cast<const float4*>(Wc + kk * 256 + 4 * tn);
-      const float4 w1 = *reinterpret_cast<const float4*>(Wc + kk * 256 + 128 + 4 * tn);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int n = 0; n < 8; ++n) acc[i][n] = fmaf(av[i], wv[n], acc[i][n]);
-    }
-    __syncthreads();   // every warp is done with this stage (and, after the last chunk, with Abuf)
-    if (threadIdx.x == 0 && ps.c + NS < ps.total) issue_chunk(a, wst, full, ps.c + NS);
-    ps.c++;
-  }
-}
-
-__device__ __forceinline__ void zero_acc(float (&acc)[8][8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int n = 0; n < 8; ++n) acc[i][n] = 0.f;
-}
-
-// Out[n][m] = act(acc + bias[n]); Out is [256][TMP] in smem
-__device__ __forceinline__ void store_acc(const float (&acc)[8][8], float* Out, const float* bias, bool relu,
-                                          int m0, int tn) {
-#pragma unroll
-  for (int jn = 0; jn < 8; ++jn) {
-    const int n = (jn < 4) ? (4 * tn + jn) : (128 + 4 * tn + jn - 4);
-    const float b = bias[n];
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[i] = acc[i][jn] + b;
-      if (relu) v[i] = fmaxf(v[i], 0.f);
-    }
-    *reinterpret_cast<float4*>(Out + n * TMP + m0) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(Out + n * TMP + m0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-}
 
 template <bool ROWLAT>
 __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant__ Fp32Args a) {
@@ -164,6 +72,12 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int f = (int)(tile / a.tiles_per_frame);
     const long long p_base = (tile % a.tiles_per_frame) * TM;
+    // training forward: slot s of `save` is [F*P][256]; this tile's rows start at grow(s)
+    const long long n_rows_total = (long long)a.n_frames * a.src.P;
+    const int rows_valid = (int)((a.src.P - p_base) < TM ? (a.src.P - p_base) : TM);
+    auto grow = [&](int slot) -> float* {
+      return a.save ? a.save + ((size_t)slot * n_rows_total + (size_t)f * a.src.P + p_base) * 256 : nullptr;
+    };
     // ---- stage the tile's inputs: positional encoding (tf_nerf.py:404-425) [+ latent rows]
     {
       const int m = tid & 63, part = tid >> 6;   // 4 threads per point, frequencies interleaved
@@ -206,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
     zero_acc(acc);
     gemm_seg(acc, PE, e_chunks, ps, a, wst, full, m0, tn);
     if (ROWLAT) gemm_seg(acc, LAT, 4, ps, a, wst, full, m0, tn);
-    store_acc(acc, X, bias0, false, m0, tn);
+    store_acc(acc, X, bias0, false, m0, tn, grow(0), rows_valid);
     __syncthreads();
     // ---- pts_linears 0..4 + ReLU                              (tf_nerf.py:265-267)
     float* in = X;
@@ -214,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
     for (int l = 0; l < 5; ++l) {
       zero_acc(acc);
       gemm_seg(acc, in, 16, ps, a, wst, full, m0, tn);
-      store_acc(acc, out, Fp + F_PTS_B + l * 256, true, m0, tn);
+      store_acc(acc, out, Fp + F_PTS_B + l * 256, true, m0, tn, grow(1 + l), rows_valid);
       __syncthreads();
       float* t = in; in = out; out = t;
     }
@@ -223,22 +137,22 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
     zero_acc(acc);
     gemm_seg(acc, PE, e_chunks, ps, a, wst, full, m0, tn);
     if (ROWLAT) gemm_seg(acc, LAT, 4, ps, a, wst, full, m0, tn);
-    store_acc(acc, X, biasS, false, m0, tn);
+    store_acc(acc, X, biasS, false, m0, tn, grow(6), rows_valid);
     __syncthreads();
     // ---- pts_linears.5 on cat([h_skip, h])                    (tf_nerf.py:281, :170-172) -> X
     zero_acc(acc);
     gemm_seg(acc, X, 16, ps, a, wst, full, m0, tn);
     gemm_seg(acc, Y, 16, ps, a, wst, full, m0, tn);
-    store_acc(acc, X, Fp + F_PTS_B + 5 * 256, true, m0, tn);
+    store_acc(acc, X, Fp + F_PTS_B + 5 * 256, true, m0, tn, grow(7), rows_valid);
     __syncthreads();
     // ---- pts_linears 6, 7
     zero_acc(acc);
     gemm_seg(acc, X, 16, ps, a, wst, full, m0, tn);
-    store_acc(acc, Y, Fp + F_PTS_B + 6 * 256, true, m0, tn);
+    store_acc(acc, Y, Fp + F_PTS_B + 6 * 256, true, m0, tn, grow(8), rows_valid);
     __syncthreads();
     zero_acc(acc);
     gemm_seg(acc, Y, 16, ps, a, wst, full, m0, tn);
-    store_acc(acc, X, Fp + F_PTS_B + 7 * 256, true, m0, tn);
+    store_acc(acc, X, Fp + F_PTS_B + 7 * 256, true, m0, tn, grow(9), rows_valid);
     __syncthreads();
     // ---- output_linear (raw, no activation)                   (tf_nerf.py:283)
     {
@@ -314,7 +228,7 @@ int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const f
 }
 
 int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, long long time_idx, int has_time,
-                         float* out, int uv_dims, int out_ch, cudaStream_t st) {
+                         float* out, float* save, int uv_dims, int out_ch, cudaStream_t st) {
   Fp32Args a{};
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
@@ -323,6 +237,7 @@ int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, lon
   a.src.uv_dims = uv_dims;
   a.src.P = n_rows;
   a.rows = x;
+  a.save = save;
   a.time_idx = time_idx;
   a.has_time = has_time;
   a.out = out;

@@ -76,6 +76,17 @@ __global__ void pack_relayout_kernel(ParamPtrs P, uint8_t* blob, Layout L, int E
   }
   for (int i = tid; i < 4; i += nth) Fp[F_OUT_B + i] = (i < out_ch) ? P.p[S2L_P_OUT_B][i] : 0.f;
 
+  // DGRAD: untransposed weights for dX = dY * W  (slot 5 = pts_linears.5[:, :256], slot 6 = pts_linears.5[:, 256:])
+  {
+    float* Dg = reinterpret_cast<float*>(blob + L.off_dgrad);
+    for (int slot = 0; slot < D_SLOTS; ++slot) {
+      const int l = slot <= 4 ? slot : (slot <= 6 ? 5 : slot - 1);
+      const int ld = (l == 5) ? 512 : 256, col0 = (slot == 6) ? 256 : 0;
+      const float* w = pts_w(P, l);
+      for (int i = tid; i < 65536; i += nth) Dg[d_slot_off(slot) + i] = w[(i >> 8) * ld + col0 + (i & 255)];
+    }
+  }
+
   // TCBIAS [9][256]: G0/G5 rows unused (per-frame folded bias), G8 = output bias padded
   for (int i = tid; i < kNumG * 256; i += nth) {
     const int g = i / 256, n = i % 256;

@@ -187,25 +187,35 @@ class TalkingFace(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def _check_inference(self, *tensors):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self._hot_params().values()):
-            raise NotImplementedError(
-                "speech2lip_b200.TalkingFace: backward of the fused MLP is not built yet (SURVEY §8(f) rank 2); "
-                "call the hot path under torch.no_grad()")
+    def _needs_grad(self, *tensors):
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self._hot_params().values())
+                                            or any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors))
 
     # ------------------------------------------------------------------ hot path
     def audio_merge_forward(self, audio):
         """tf_nerf.py:197-213.  audio: [B,16,29] or [B,29,16] -> [B,64]."""
-        self._check_inference()
+        if self._needs_grad(audio):
+            # training: AudioNet is 67 k MAC per frame — its forward/backward stay on autograd (SURVEY §7 step 8);
+            # the result feeds the fused MLP's autograd.Function through the latent columns of rgb_forward's input
+            x = audio if audio.shape[2] == 16 else audio.permute(0, 2, 1)
+            for i in (0, 2, 4, 6):
+                # Conv1d(k3,s2,p1) as unfold + matmul: true-fp32 GEMMs in both directions (cuDNN would pick TF32 by default)
+                conv = self.encoder_conv[i]
+                cols = F.pad(x, (1, 1)).unfold(2, 3, 2)                                  # [B,C,T/2,3]
+                cols = cols.permute(0, 2, 1, 3).reshape(x.shape[0], cols.shape[2], -1)   # [B,T/2,C*3]
+                x = F.leaky_relu(cols @ conv.weight.reshape(conv.weight.shape[0], -1).t() + conv.bias, 0.02).permute(0, 2, 1)
+            return self.encoder_fc1(x.squeeze(-1))
         latent, _ = R.audio_encode(self.packed_weights(), audio, None, want_latent=True, want_bias=False)
         return latent
 
     def rgb_forward(self, uv_audio_pts, time_pts=None, head_pose_pts=None, rgb_pts=None, lms_pts=None, text_pts=None):
         """tf_nerf.py:225-285.  uv_audio_pts [N, uv_dims+64]; time_pts: only element 0 is used (tf_nerf.py:439)."""
-        self._check_inference()
         t = None
         if time_pts is not None:
             t = int(torch.as_tensor(time_pts).reshape(-1)[0].item())
+        if self._needs_grad(uv_audio_pts):
+            from .autograd import rgb_forward_train      # fused fp32 forward (saves activations) + fused dgrad kernel
+            return rgb_forward_train(self, uv_audio_pts, t)
         return R.rgb_forward_rows(self.packed_weights(), uv_audio_pts, t)
 
     def renderer(self, precision="bf16x3"):

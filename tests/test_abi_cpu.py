@@ -104,3 +104,18 @@ def test_post_fusion_runs_on_cpu():
     with torch.no_grad():
         recon, merged, canon = m.post_fusion2_onlylip(lip, face, face.clone(), mask, 20, 20, coord)
     assert recon.shape == (B, H, W, 3) and merged.shape == (B, H, W, 3) and canon.shape == (B, H, W, 3)
+
+
+def test_training_mode_audionet_matches_oracle_on_cpu():
+    """in grad mode AudioNet runs as unfold+matmul on autograd (true fp32): same numbers as the oracle."""
+    from oracle import s2l_oracle as O
+    from oracle import synth
+    from speech2lip_b200 import TalkingFace
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = TalkingFace(device=torch.device("cpu"), cfg=cfg).train()
+    sd = synth.make_state_dict(0, "kaiming")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    a = torch.from_numpy(synth.make_audio(3, seed=1))
+    ref = O.audio_merge_forward(O.to_torch_sd(sd), a)
+    assert (m.audio_merge_forward(a) - ref).abs().max().item() < 1e-6
+    assert (m.audio_merge_forward(a.permute(0, 2, 1).contiguous()) - ref).abs().max().item() < 1e-6

@@ -338,8 +338,8 @@ def test_talking_face_drop_in(S, golden):
         m.output_linear.bias.add_(1.0)
         out2 = m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()))
     assert abs((out2 - out).mean().item() - 1.0) < 1e-5
-    with pytest.raises(NotImplementedError):
-        m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()))        # grad mode: backward not built yet
+    out3 = m.rgb_forward(x, time_pts=torch.tensor([5], device=dev()))     # grad mode: fused training forward
+    assert out3.requires_grad and maxabs(out3.detach().cpu(), out2.cpu()) < 1e-6
     rgb = m.renderer("bf16x3").render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([5]), H, W)
     assert maxabs((rgb[0] - 1.0).cpu(), g["rgb"]) < PARITY_TOL
 
@@ -378,3 +378,66 @@ def test_talking_face_post_fusion_uses_kernel(S, golden):
     assert _cabi.lib().s2l_launch_count(0) == 2, "post-fusion did not go through the CUDA kernels"
     assert recon.shape == fused.shape == (2, 40, 40, 3)
     assert maxabs(fused.cpu(), g["fused"]) < 2e-6 and maxabs(canon.cpu(), g["canon"]) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ next row: backward (fp32 exact)
+@pytest.mark.parametrize("kind", ["default", "kaiming"])
+def test_training_backward_vs_oracle_autograd(S, kind):
+    """SURVEY 8(f) rank 2 (first step): loss.backward() through audio_merge_forward -> rgb_forward on the drop-in module
+    (fused fp32 forward that saves activations + fused dgrad kernel + GEMM wgrads) vs torch autograd of the oracle."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg).to(dev()).train()
+    sd_np = synth.make_state_dict(0, kind)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()}, strict=False)
+    H, W, idx = 9, 13, 4                                     # 117 rows: not a multiple of the 64-row tile
+    audio = torch.from_numpy(synth.make_audio(1, seed=21))
+    gen = torch.Generator().manual_seed(5)
+    wgt = torch.randn(H * W, 3, generator=gen)
+    coords = O.get_coords(W, H)
+
+    # --- candidate: exactly the call sequence of training.py:165-236 (one tap)
+    lat = m.audio_merge_forward(audio.to(dev())).unsqueeze(1).tile(1, H * W, 1).view(-1, 64)
+    x = torch.cat([coords.to(dev()), lat], -1)
+    out = m.rgb_forward(x, time_pts=torch.tensor([idx], device=dev()))
+    loss = (out * wgt.to(dev())).sum()
+    loss.backward()
+
+    # --- oracle: same arithmetic under torch autograd on the CPU (float64 for a clean reference)
+    sd = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in sd_np.items()}
+    lat_o = O.audio_merge_forward(sd, audio.double()).unsqueeze(1).tile(1, H * W, 1).view(-1, 64)
+    out_o = O.rgb_forward(sd, torch.cat([coords.double(), lat_o], -1), torch.tensor([idx]))
+    (out_o * wgt.double()).sum().backward()
+
+    assert maxabs(out.detach().cpu(), out_o.detach()) < tol_fp32(kind)
+    worst = 0.0
+    for name, p in m.named_parameters():
+        if name in sd_np:
+            assert p.grad is not None, "no gradient reached %s" % name
+            ref = sd[name].grad
+            scale = float(ref.abs().max()) + 1e-12
+            rel = maxabs(p.grad.cpu(), ref) / scale
+            worst = max(worst, rel)
+            assert rel < 2e-4, "%s: relative grad error %.3e" % (name, rel)
+    print("backward %s: worst relative grad error %.3e" % (kind, worst))
+    # the dead / out-of-path parameters must not receive gradients
+    assert m.coord_linears[0].weight.grad is None
+
+
+def test_training_step_changes_output_and_repacks(S):
+    """an optimizer step updates the parameters in place -> the packed blob must follow (tensor._version tracking)."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg).to(dev()).train()
+    opt = torch.optim.Adam([p for n, p in m.named_parameters() if not n.startswith(("post_fusion", "canonical", "coord_"))], lr=1e-3)
+    audio = torch.from_numpy(synth.make_audio(1, seed=2)).to(dev())
+    coords = O.get_coords(8, 8).to(dev())
+    target = torch.full((64, 3), 0.5, device=dev())
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        lat = m.audio_merge_forward(audio).expand(64, -1)
+        out = m.rgb_forward(torch.cat([coords, lat], -1), time_pts=torch.tensor([0], device=dev()))
+        loss = ((out - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
