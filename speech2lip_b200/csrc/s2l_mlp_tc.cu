@@ -59,7 +59,16 @@ struct TcArgs {
   int out_ch;
   int n_frames;
   long long tiles_per_frame;
+  long long* dbg;            // S2L_TIMELINE builds only: event log of CTA 0 (tools/tc_timeline.py)
 };
+
+// Cycle-stamped event log for pipeline analysis; compiled out unless -DS2L_TIMELINE.
+#ifdef S2L_TIMELINE
+#define TL(role, code) do { if (a.dbg && blockIdx.x == 0 && it == 2) { \
+    long long* _p = a.dbg + (role) * 2048; long long _n = _p[0]; if (_n < 1000) { _p[1 + 2 * _n] = (code); _p[2 + 2 * _n] = clock64(); _p[0] = _n + 1; } } } while (0)
+#else
+#define TL(role, code) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------ tcgen05 wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -243,6 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll 1
           for (int h = 0; h < nh; ++h) {
             const uint32_t d_addr = d_region + (uint32_t)h * 128u;
+            TL(0, 1000 + g * 10 + h);                       // MMA thread starts half h of layer g
 #pragma unroll 1
             for (int kc = 0; kc < nkc; ++kc) {
               const bool is_pe = (g == 0) || (g == 5 && kc == 0);
@@ -296,6 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               }
             }
             umma_commit(&acc_full[h]);           // accumulator half h of layer g complete
+            TL(0, 5000 + g * 10 + h);
           }
           if (g == 5) umma_commit(&pe_empty[buf]);   // last reader of this tile's PE image
           rp ^= 1;
@@ -376,6 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           mbar_wait_wd(&acc_full[hh], acc_par[hh], 700 + hh);
           acc_par[hh] ^= 1;
           tc_fence_after();
+          if (tid == 256) TL(1, 7000 + g * 10 + hh);       // epilogue observed accumulator half
           // both quarters of the half are loaded up front so the second load's latency hides behind the
           // first quarter's conversion; each quarter is released to the MMA thread as soon as it is stored
           const uint32_t taddr0 = d_region + lane_sel + (uint32_t)(hh * 128 + half * 32);
@@ -410,6 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&epi_done[q]);
+            if (tid == 256) TL(1, 9000 + g * 10 + q);      // quarter released to the MMA thread
           }
         }
         if (g == 5) mbar_arrive(&pe_empty[buf]);      // this thread no longer reads fbias_s[buf]
@@ -464,6 +477,9 @@ static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   return check_launch("mlp_tc_kernel") ? 0 : 5;
 }
 
+static long long* g_timeline = nullptr;
+extern "C" void s2l_debug_set_timeline(long long* buf) { g_timeline = buf; }     // debug builds (tools/tc_timeline.py)
+
 int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
                   int npass, cudaStream_t st) {
   TcArgs a{};
@@ -475,6 +491,7 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   a.out_ch = out_ch;
   a.n_frames = n_frames;
   a.tiles_per_frame = (src.P + TC_TM - 1) / TC_TM;
+  a.dbg = g_timeline;
   const long long n_tiles = a.tiles_per_frame * n_frames;
   if (n_tiles == 0) return 0;
   if (src.uv_dims == 2) return npass == 3 ? launch_tc_impl<3, 2>(a, n_tiles, st) : launch_tc_impl<1, 2>(a, n_tiles, st);

@@ -1,0 +1,33 @@
+"""Debug tool (S2L_TIMELINE build only): dumps a cycle-stamped event log of CTA 0's third tile."""
+import ctypes as C, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import speech2lip_b200 as s2l
+from speech2lip_b200 import _cabi
+from oracle import synth
+prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+dev = torch.device("cuda:0")
+sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
+w = s2l.PackedWeights(sd)
+r = s2l.LipRenderer(w, prec)
+audio = torch.from_numpy(synth.make_audio(8, seed=1)).to(dev)
+idx = torch.arange(8)
+lib = _cabi.lib()
+lib.s2l_debug_set_timeline.argtypes = [C.c_void_p]
+for _ in range(2):
+    r.render_frames(audio, idx, 256, 256)
+buf = torch.zeros(3 * 2048, dtype=torch.int64, device=dev)
+lib.s2l_debug_set_timeline(C.c_void_p(buf.data_ptr()))
+r.render_frames(audio, idx, 256, 256)
+torch.cuda.synchronize()
+lib.s2l_debug_set_timeline(None)
+b = buf.cpu().tolist()
+ev = []
+for role in range(3):
+    n = b[role * 2048]
+    for i in range(n):
+        ev.append((b[role * 2048 + 2 + 2 * i], role, b[role * 2048 + 1 + 2 * i]))
+ev.sort()
+t0 = ev[0][0]
+for t, role, code in ev:
+    print("%8d  %s  %d" % (t - t0, ["MMA ", "EPI8", "EPI12"][role], code))
