@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 FLOP_PER_POINT = {"volumetric": 1_246_208, "plain": 1_224_192, "ensemble4": 1_224_192}   # SURVEY §8(d), algorithmic
+ISSUED_MAC_PER_POINT = 495_616      # folded tensor-core layer program, per MMA pass
 METRIC = "lip frames/sec @256x256,64 samples/ray"
 
 
@@ -338,7 +339,12 @@ def run_gpu_arm(a):
                          "traffic": None, "kernel": "mlp_tc_kernel" if tensor_bound else "mlp_fp32_kernel",
                          "kernel_ms_per_launch": ker_ms / a.steps, "flop_per_point_algorithmic": FLOP_PER_POINT[a.mode],
                          "mma_multiplier": 3 if a.precision == "bf16x3" else 1, "peak_source": peak_src,
-                         "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None},
+                         "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None,
+                         # tensor-pipe view: MMA math actually issued (3 bf16 MMAs per product in the parity mode, after folding)
+                         "issued_mma_tflops": (float(F) * P * ISSUED_MAC_PER_POINT * 2 * (3 if a.precision == "bf16x3" else 1)
+                                               / (ker_ms / a.steps * 1e-3) / 1e12) if tensor_bound else None,
+                         "issued_mma_frac_of_peak": (float(F) * P * ISSUED_MAC_PER_POINT * 2 * (3 if a.precision == "bf16x3" else 1)
+                                                     / (ker_ms / a.steps * 1e-3) / 1e12 / peak) if tensor_bound else None},
             "clocks": clocks, "checksum": checksum, "finite": finite,
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -174,7 +174,10 @@ int launch_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts,
     for (int j = 0; j < 16; ++j) b.core.prog.off[n++] = dg + d_slot_off(order[s]) + j * CHUNK_FLOATS;
   b.core.prog.n_chunks = n;
   const size_t smem = sizeof(float) * (size_t)(2 * 256 * TMP + NS * CHUNK_FLOATS);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     if (cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("mlp_bwd: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));

@@ -214,7 +214,10 @@ int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const f
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = fp32_smem_bytes(false);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     if (cudaFuncSetAttribute(mlp_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("mlp_fp32: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
@@ -250,7 +253,10 @@ int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, lon
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = fp32_smem_bytes(true);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     if (cudaFuncSetAttribute(mlp_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       set_error("mlp_fp32_rows: cannot opt in to %zu B of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));

@@ -461,7 +461,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
 template <int NPASS, int UVD>
 static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
       set_error("mlp_tc: cannot opt in to %d B of shared memory: %s", TC_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
