@@ -94,7 +94,11 @@ class FusedMLPRows(torch.autograd.Function):
 
 def rgb_forward_train(module, x, time_idx):
     """x [N, uv_dims+64] (latent columns may require grad), module = speech2lip_b200.TalkingFace."""
-    sd = dict(module.named_parameters())
+    sd = module._hot_params()
     params = [sd[n] for n in param_order()]
-    div = torch.exp(torch.arange(0, 20, 2, dtype=torch.float) * -(torch.log(torch.tensor(10000.0)).item() / 20)).to(x.device)
+    div = module.__dict__.get("_div_term")
+    if div is None or div.device != x.device:
+        import math
+        div = torch.exp(torch.arange(0, 20, 2, dtype=torch.float) * -(math.log(10000.0) / 20)).to(x.device)   # tf_nerf.py:431-432
+        module.__dict__["_div_term"] = div
     return FusedMLPRows.apply(x, time_idx, module.packed_weights(), div, *params)

@@ -172,7 +172,13 @@ class TalkingFace(nn.Module):
 
     # ------------------------------------------------------------------ packed weights (kernel layout)
     def _hot_params(self):
-        return {k: v for k, v in self.state_dict(keep_vars=True).items() if k.startswith(_HOT_PREFIXES)}
+        # Parameter objects are stable (load_state_dict / optimizers update them in place), so the name -> tensor
+        # map is built once; rebuilt only if a parameter object was replaced (e.g. module.to(dtype) tricks).
+        cache = self.__dict__.get("_hot_cache")
+        if cache is None or cache["fc_uv.weight"] is not self.fc_uv.weight or cache["pts_linears.7.bias"] is not self.pts_linears[7].bias:
+            cache = {k: v for k, v in self.named_parameters() if k.startswith(_HOT_PREFIXES)}
+            self.__dict__["_hot_cache"] = cache
+        return cache
 
     def packed_weights(self):
         """PackedWeights for the current parameter values; re-packed when any hot-path tensor changed

@@ -441,3 +441,22 @@ def test_training_step_changes_output_and_repacks(S):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+def test_config4_512x512x128_properties(S):
+    """BASELINE.json config 4 geometry (512x512 rays x 128 samples = 33.5 M point evals, one frame): the tensor-core
+    parity path against the fp32 exact path over ALL rays, plus compositing invariants (S equals the 128-point tile)."""
+    H = W = 512
+    Sn = 128
+    audio = torch.from_numpy(synth.make_audio(1, seed=13)).to(dev())
+    ro, rd = S.get_rays(H, W, 1200.0, torch.eye(4)[:3].to(dev()))
+    z = O.z_samples(Sn).to(dev())
+    w = packed(S, "trained", 3, 4)
+    a = S.LipRenderer(w, "bf16x3").render_frames(audio, torch.tensor([7]), H, W, mode="volumetric", rays_o=ro, rays_d=rd,
+                                                 z_vals=z, return_aux=True)
+    b = S.LipRenderer(w, "fp32").render_frames(audio, torch.tensor([7]), H, W, mode="volumetric", rays_o=ro, rays_d=rd, z_vals=z)
+    err = (a[0] - b).abs().max().item()
+    print("512x512x128: tc-vs-fp32 maxabs %.3e" % err)
+    assert err < PARITY_TOL
+    assert torch.isfinite(a[0]).all() and (a[1] >= 0).all() and (a[1].sum(-1) <= 1 + 1e-4).all()
+    assert O.psnr(a[0].cpu(), b.cpu()) > 80.0
