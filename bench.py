@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="volumetric", choices=["volumetric", "plain", "ensemble4"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16x1", "fp32"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16x1", "fp32", "fp16f8"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
@@ -326,7 +326,7 @@ def run_gpu_arm(a):
             "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": {"bf16x3": "bf16x3-split (fp32 accumulate)", "bf16x1": "bf16", "fp32": "f32"}[a.precision], "data": "synthetic",
+            "dtype": {"bf16x3": "bf16x3-split (fp32 accumulate)", "bf16x1": "bf16", "fp32": "f32", "fp16f8": "fp16 + 2x fp8 corrections (fp32 accumulate)"}[a.precision], "data": "synthetic",
             "config": {"workload": workload_name(a), "mode": a.mode, "precision": a.precision,
                        "points_per_frame": P, "weights": "synthetic kaiming-normal ('trained-like'), seed 0",
                        "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
@@ -338,12 +338,12 @@ def run_gpu_arm(a):
             "roofline": {"bound": "tensor" if tensor_bound else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": None, "kernel": "mlp_tc_kernel" if tensor_bound else "mlp_fp32_kernel",
                          "kernel_ms_per_launch": ker_ms / a.steps, "flop_per_point_algorithmic": FLOP_PER_POINT[a.mode],
-                         "mma_multiplier": 3 if a.precision == "bf16x3" else 1, "peak_source": peak_src,
+                         "mma_multiplier": {"bf16x3": 3, "fp16f8": 2}.get(a.precision, 1), "peak_source": peak_src,
                          "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None,
                          # tensor-pipe view: MMA math actually issued (3 bf16 MMAs per product in the parity mode, after folding)
-                         "issued_mma_tflops": (float(F) * P * ISSUED_MAC_PER_POINT * 2 * (3 if a.precision == "bf16x3" else 1)
+                         "issued_mma_tflops": (float(F) * P * ISSUED_MAC_PER_POINT * 2 * {"bf16x3": 3, "fp16f8": 2}.get(a.precision, 1)
                                                / (ker_ms / a.steps * 1e-3) / 1e12) if tensor_bound else None,
-                         "issued_mma_frac_of_peak": (float(F) * P * ISSUED_MAC_PER_POINT * 2 * (3 if a.precision == "bf16x3" else 1)
+                         "issued_mma_frac_of_peak": (float(F) * P * ISSUED_MAC_PER_POINT * 2 * {"bf16x3": 3, "fp16f8": 2}.get(a.precision, 1)
                                                      / (ker_ms / a.steps * 1e-3) / 1e12 / peak) if tensor_bound else None},
             "clocks": clocks, "checksum": checksum, "finite": finite,
         }

@@ -55,7 +55,9 @@ enum {
 enum {
   S2L_PREC_FP32   = 0,  /* CUDA-core fp32 FFMA, literal (unfolded) layer order: the exact path      */
   S2L_PREC_BF16X3 = 1,  /* tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (parity)   */
-  S2L_PREC_BF16X1 = 2   /* tcgen05 single bf16 pass (fast, NOT within the 1e-3 parity bar)          */
+  S2L_PREC_BF16X1 = 2,  /* tcgen05 single bf16 pass (fast, NOT within the 1e-3 parity bar)          */
+  S2L_PREC_FP16F8 = 3   /* tcgen05 fp16 main product + two fp8 (e4m3/e5m2) correction products, fp32 accumulate:
+                           2 bf16-MMA equivalents per product, ~3e-4 max-abs on O(8) outputs (parity)  */
 };
 
 /* How the kernel obtains the coordinates of point-evaluation p of frame f. */

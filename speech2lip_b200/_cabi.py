@@ -11,9 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("S2L_LIB_PATH") or os.path.join(_HERE, "csrc", "libs2l_b200.so")   # env override: debug builds only
 
 NUM_PARAMS = 42
-PREC_FP32, PREC_BF16X3, PREC_BF16X1 = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16X1, PREC_FP16F8 = 0, 1, 2, 3
 PTS_GRID, PTS_GRID_ENS4, PTS_RAYS, PTS_EXPLICIT = 0, 1, 2, 3
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16x1": PREC_BF16X1}
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16x1": PREC_BF16X1, "fp16f8": PREC_FP16F8}
 
 # reference state_dict names in S2L_P_* order (include/speech2lip_b200.h)
 PARAM_NAMES = (

@@ -109,6 +109,7 @@ extern "C" int32_t s2l_mlp_fwd(const void* blob, const S2LGeom* geom, const floa
     case S2L_PREC_FP32: return launch_mlp_fp32(blob, src, geom->n_frames, frame_bias, raw_out, geom->out_ch, st);
     case S2L_PREC_BF16X3: return launch_mlp_tc(blob, src, geom->n_frames, frame_bias, raw_out, geom->out_ch, 3, st);
     case S2L_PREC_BF16X1: return launch_mlp_tc(blob, src, geom->n_frames, frame_bias, raw_out, geom->out_ch, 1, st);
+    case S2L_PREC_FP16F8: return launch_mlp_tc(blob, src, geom->n_frames, frame_bias, raw_out, geom->out_ch, 2, st);
     default: set_error("s2l_mlp_fwd: unknown precision %d", precision); return 2;
   }
 }

@@ -87,8 +87,14 @@ constexpr int D_SLOTS = 9;
 __host__ __device__ constexpr int d_slot_off(int slot) { return slot * 65536; }
 constexpr int D_TOTAL = D_SLOTS * 65536;
 
+// ---- TCW8 section: same granule order/size as TCW, for the fp16 + fp8-correction arithmetic (S2L_PREC_FP16F8):
+//      plane 0 = fp16(W) [rows][64 K] SW128;  plane 1 = e5m2(fp16(W) * 2^-kScaleA) [rows][64 K] SW64  followed by
+//      e4m3((W - fp16(W)) * 2^kScaleW) [rows][64 K] SW64.
+constexpr int kScaleA = 8;      // activation residual (A - fp16(A)) is scaled by 2^+8 before e4m3; W1 copy by 2^-8
+constexpr int kScaleW = 10;     // weight residual (W - fp16(W)) is scaled by 2^+10 before e4m3; A1 copy by 2^-10
+
 struct Layout {
-  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, total;
+  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, off_tcw8, total;
 };
 __host__ __device__ inline Layout blob_layout() {
   Layout L;
@@ -100,6 +106,7 @@ __host__ __device__ inline Layout blob_layout() {
   L.off_tcbias = o; o = al(o + sizeof(float) * kNumG * 256);
   L.off_tcw = o;    o = al(o + kTcwBytes);
   L.off_dgrad = o;  o = al(o + sizeof(float) * D_TOTAL);
+  L.off_tcw8 = o;   o = al(o + kTcwBytes);
   L.total = o;
   return L;
 }
@@ -109,6 +116,11 @@ __host__ __device__ inline int pe_dim(int uv_dims) { return uv_dims + 2 * kMulti
 // byte offset of element (row n, k) inside a K-major 128B-swizzled [rows][64] bf16 tile
 __host__ __device__ inline int sw128_off(int n, int k) {
   return (n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2;
+}
+
+// byte offset of element (row n, k) inside a K-major 64B-swizzled [rows][64] 8-bit tile (8-row atoms of 512 B)
+__host__ __device__ inline int sw64_off(int n, int k) {
+  return (n >> 3) * 512 + (n & 7) * 64 + ((((k >> 4) ^ ((n >> 1) & 3)) & 3) << 4) + (k & 15);
 }
 
 // ------------------------------------------------------------------ error / launch bookkeeping (host)

@@ -25,10 +25,16 @@
 //
 // Precision: NPASS = 3 issues hi*hi + lo*hi + hi*lo (bf16 split, fp32 accumulate) ~ 2^-17 relative
 // per product — this is the parity mode (<= 1e-3 max-abs).  NPASS = 1 issues hi*hi only.
+// NPASS = 2 ("fp16f8") is the cheaper parity mode: an exact fp16 x fp16 main product plus the two first-order
+// corrections (A - fp16 A) * W and A * (W - fp16 W) evaluated on the fp8 tensor path (kind::f8f6f4, twice the
+// bf16 rate) with power-of-two pre-scaling (e4m3 for the residuals, e5m2 for the full-range factors):
+// 1 + 0.5 + 0.5 = 2 bf16-MMA equivalents per product instead of 3, ~2^-15 relative per product.
 //
 // Warp roles (512 threads): w0 weight producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
 // w4-7 PE producers, w8-15 epilogue (two warps per TMEM lane quadrant, 32 columns each).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cstdio>
 #include "s2l_common.cuh"
 #include "s2l_points.cuh"
@@ -102,6 +108,28 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// kind::f16 with fp16 operands / kind::f8f6f4 instruction descriptors (D = f32, K-major, M = 128, N = n)
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_f8(int n, uint32_t a_fmt, uint32_t b_fmt) {   // 0 = e4m3, 1 = e5m2
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma8_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -159,6 +187,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);                // .x (low 16 bits) = lo
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// four floats -> four fp8 bytes, element i in byte i
+__device__ __forceinline__ uint32_t pack_fp8x4(float a, float b, float c, float d, __nv_fp8_interpretation_t kind) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, kind);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, kind);
+  return lo | (hi << 16);
+}
+
 template <int NPASS, int UVD>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -175,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = a.tiles_per_frame * a.n_frames;
-  const uint8_t* tcw = a.blob + a.L.off_tcw;
+  const uint8_t* tcw = a.blob + (NPASS == 2 ? a.L.off_tcw8 : a.L.off_tcw);
 
   if (tid == 0) {
     for (int s = 0; s < NSTG; ++s) {
@@ -238,16 +277,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       long long it = 0;
       constexpr uint32_t kDescHi = 0x40004040u;   // SBO=64 | version=1 | SWIZZLE_128B  (upper descriptor word)
       auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi << 32) | lo; };
+      constexpr uint32_t kDescHi64 = 0x80004020u; // SBO=32 (512 B atoms) | version=1 | SWIZZLE_64B: 8-bit operands, 64 K per row
+      auto mk64 = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi64 << 32) | lo; };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int buf = (int)(it & 1);
         const uint32_t pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
         const uint32_t pe_lo = pe_hi + (PE_PLANE >> 4);
+        const uint32_t pe_e5 = pe_lo, pe_e4 = pe_lo + (PE_PLANE >> 5);      // NPASS == 2: [fp16 16 KB | e5m2 8 KB | e4m3 8 KB]
 #pragma unroll 1
         for (int g = 0; g < kNumG; ++g) {
           const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
           const uint32_t a_region = tmem_base + (rp ? 0u : 256u);
           const int nh = (g == 8) ? 1 : 2;
-          const uint32_t idesc = (g == 8) ? idesc_bf16(kOutPad) : idesc_bf16(kGranRows);
+          const int n_mma = (g == 8) ? kOutPad : kGranRows;
+          const uint32_t idesc = (NPASS == 2) ? idesc_f16(n_mma) : idesc_bf16(n_mma);
+          const uint32_t idesc_rw = idesc_f8(n_mma, 0u, 1u);     // (A - fp16 A) [e4m3] x fp16(W) [e5m2]
+          const uint32_t idesc_wr = idesc_f8(n_mma, 1u, 0u);     // fp16(A) [e5m2] x (W - fp16 W) [e4m3]
           const int nkc = g_nkc(g);
 #pragma unroll 1
           for (int h = 0; h < nh; ++h) {
@@ -288,6 +333,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               }
               umma_commit(&b_empty[stage]);      // stage reusable once these MMAs retire
               if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+              // ---- fp8 correction plane: [e5m2 fp16(W)*2^-8 | e4m3 (W-fp16 W)*2^10], two K=32 steps per 64-K chunk
+              if (NPASS == 2) {
+                mbar_wait_wd(&b_full[stage], phase, 450 + stage);
+                tc_fence_after();
+                const int plane8 = ((g == 8) ? kOutPlane : kGranPlane) / 2;
+                const uint32_t b5 = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
+                const uint32_t b4 = b5 + (uint32_t)(plane8 >> 4);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                  if (is_pe) {
+                    umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b5 + 2 * t), idesc_rw, 1u);
+                    umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
+                  } else {
+                    // A chunk layout in TMEM for this mode, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
+                    umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b5 + 2 * t), idesc_rw, 1u);
+                    umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
+                  }
+                }
+                umma_commit(&b_empty[stage]);
+                if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+              }
               // ---- lo weight plane: A_hi*W_lo
               if (NPASS == 3) {
                 mbar_wait_wd(&b_full[stage], phase, 450 + stage);
@@ -344,6 +410,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       uint8_t* hi_base = smem + SM_PE + buf * PE_BUF;
       uint8_t* lo_base = hi_base + PE_PLANE;
       const int row_off = (r >> 3) * 1024 + (r & 7) * 128;
+      if (NPASS == 2) {
+        // fp16 main image (SW128) + e5m2(fp16(e) * 2^-kScaleW) and e4m3((e - fp16 e) * 2^kScaleA) images (SW64)
+        constexpr float kDn = 1.0f / (float)(1 << kScaleW), kUp = (float)(1 << kScaleA);
+        uint8_t* e5_base = lo_base;
+        uint8_t* e4_base = lo_base + PE_PLANE / 2;
+        const int row_off64 = (r >> 3) * 512 + (r & 7) * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                 // 16 K-elements per 16-byte fp8 chunk
+          uint32_t w5[4], w4[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {               // two 8-element fp16 chunks
+            uint32_t h[4];
+            float f[8], rs[8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float v0 = e[16 * c + 8 * u + 2 * t], v1 = e[16 * c + 8 * u + 2 * t + 1];
+              const __half2 hh = __floats2half2_rn(v0, v1);
+              h[t] = *reinterpret_cast<const uint32_t*>(&hh);
+              const float2 back = __half22float2(hh);
+              f[2 * t] = back.x; f[2 * t + 1] = back.y;
+              rs[2 * t] = v0 - back.x; rs[2 * t + 1] = v1 - back.y;
+            }
+            const int j = 2 * c + u;
+            *reinterpret_cast<uint4*>(hi_base + row_off + ((j ^ (r & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              w5[2 * u + t] = pack_fp8x4(f[4 * t] * kDn, f[4 * t + 1] * kDn, f[4 * t + 2] * kDn, f[4 * t + 3] * kDn, __NV_E5M2);
+              w4[2 * u + t] = pack_fp8x4(rs[4 * t] * kUp, rs[4 * t + 1] * kUp, rs[4 * t + 2] * kUp, rs[4 * t + 3] * kUp, __NV_E4M3);
+            }
+          }
+          const int off64 = row_off64 + ((c ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(e5_base + off64) = make_uint4(w5[0], w5[1], w5[2], w5[3]);
+          *reinterpret_cast<uint4*>(e4_base + off64) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint32_t h[4], l[4];
@@ -357,6 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int off = row_off + ((j ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
         if (NPASS == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
       }
       {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
@@ -401,6 +503,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             const uint32_t taddr = taddr0 + (uint32_t)(qq * 64);
             const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + half * 32);
             uint32_t o[32];
+            if (NPASS == 2) {
+              // [fp16 x 32 (16 cols) | e5m2(fp16(x) * 2^-kScaleW) x 32 (8 cols) | e4m3((x - fp16 x) * 2^kScaleA) x 32 (8 cols)]
+              constexpr float kDn = 1.0f / (float)(1 << kScaleW), kUp = (float)(1 << kScaleA);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bb = b4[j4];
+                const uint32_t* v = qq ? vb : va;
+                const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
+                const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
+                const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
+                const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
+                const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                o[2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
+                o[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                o[16 + j4] = pack_fp8x4(f01.x * kDn, f01.y * kDn, f23.x * kDn, f23.y * kDn, __NV_E5M2);
+                o[24 + j4] = pack_fp8x4((x0 - f01.x) * kUp, (x1 - f01.y) * kUp, (x2 - f23.x) * kUp, (x3 - f23.y) * kUp, __NV_E4M3);
+              }
+            } else
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 bb = b4[j4];
@@ -417,7 +538,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 o[16 + 2 * j4 + 1] = pack_bf16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u));
               }
             }
-            if (NPASS == 3) tmem_st32(taddr, o);
+            if (NPASS != 1) tmem_st32(taddr, o);
             else tmem_st16(taddr, o);
             tmem_st_wait();
             tc_fence_before();
@@ -497,8 +618,10 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   a.dbg = g_timeline;
   const long long n_tiles = a.tiles_per_frame * n_frames;
   if (n_tiles == 0) return 0;
-  if (src.uv_dims == 2) return npass == 3 ? launch_tc_impl<3, 2>(a, n_tiles, st) : launch_tc_impl<1, 2>(a, n_tiles, st);
-  if (src.uv_dims == 3) return npass == 3 ? launch_tc_impl<3, 3>(a, n_tiles, st) : launch_tc_impl<1, 3>(a, n_tiles, st);
+  if (src.uv_dims == 2)
+    return npass == 3 ? launch_tc_impl<3, 2>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 2>(a, n_tiles, st) : launch_tc_impl<1, 2>(a, n_tiles, st);
+  if (src.uv_dims == 3)
+    return npass == 3 ? launch_tc_impl<3, 3>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 3>(a, n_tiles, st) : launch_tc_impl<1, 3>(a, n_tiles, st);
   set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims);
   return 2;
 }

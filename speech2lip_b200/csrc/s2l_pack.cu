@@ -2,6 +2,8 @@
 // Replaces the parameter inventory of TalkingFace.__init__ (tf_nerf.py:85-172) on the device side.
 #include <cmath>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "s2l_common.cuh"
 
 namespace s2l {
@@ -156,6 +158,14 @@ __global__ void pack_tcw_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch
   const int off = sw128_off(n, k);
   *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
   *reinterpret_cast<__nv_bfloat16*>(base + plane + off) = lo;
+  // ---- TCW8: fp16 main operand + two scaled fp8 correction operands (see s2l_common.cuh)
+  uint8_t* base8 = blob + L.off_tcw8 + g_layer_off(g) + (size_t)gi * (2 * plane);
+  const __half w1 = __float2half_rn(v);
+  const float w1f = __half2float(w1), w2f = v - w1f;
+  *reinterpret_cast<__half*>(base8 + off) = w1;
+  const int off8 = sw64_off(n, k);
+  base8[plane + off8] = (uint8_t)__nv_cvt_float_to_fp8(w1f * (1.0f / (float)(1 << kScaleA)), __NV_SATFINITE, __NV_E5M2);
+  base8[plane + plane / 2 + off8] = (uint8_t)__nv_cvt_float_to_fp8(w2f * (float)(1 << kScaleW), __NV_SATFINITE, __NV_E4M3);
 }
 
 }  // namespace s2l
