@@ -340,16 +340,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const int plane8 = ((g == 8) ? kOutPlane : kGranPlane) / 2;
                 const uint32_t b5 = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
                 const uint32_t b4 = b5 + (uint32_t)(plane8 >> 4);
+                // same-format MMAs are issued back to back (operand formats live in the instruction descriptor)
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                  if (is_pe) {
-                    umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b5 + 2 * t), idesc_rw, 1u);
-                    umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
-                  } else {
-                    // A chunk layout in TMEM for this mode, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
-                    umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b5 + 2 * t), idesc_rw, 1u);
-                    umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
-                  }
+                  if (is_pe) umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b5 + 2 * t), idesc_rw, 1u);
+                  // A chunk layout in TMEM for this mode, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
+                  else umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b5 + 2 * t), idesc_rw, 1u);
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                  if (is_pe) umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
+                  else umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
                 }
                 umma_commit(&b_empty[stage]);
                 if (++stage == NSTG) { stage = 0; phase ^= 1u; }

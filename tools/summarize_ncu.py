@@ -68,7 +68,7 @@ for r in data:
     if m:
         mn[m.group(1).split(".")[0]] += int(r[ix["Instructions Executed"]] or 0)
 out += ["SASS mnemonics proving the Blackwell path (executed warp-instructions): " +
-        ", ".join("%s=%d" % (k, mn[k]) for k in ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "SYNCS") if k in mn), ""]
+        ", ".join("%s=%d" % (k, mn[k]) for k in ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "SYNCS") if k in mn), ""]
 out += ["top instructions by samples:", "", "```"]
 for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:12]:
     out.append("%7s  exec=%-10s %s" % (r[ix["# Samples"]], r[ix["Instructions Executed"]], r[ix["Source"]][:90]))
