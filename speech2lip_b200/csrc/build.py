@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["s2l_capi.cu", "s2l_pack.cu", "s2l_audio.cu", "s2l_mlp_fp32.cu", "s2l_mlp_tc.cu", "s2l_reduce.cu", "s2l_postfusion.cu", "s2l_mlp_bwd.cu"]
+SOURCES = ["s2l_capi.cu", "s2l_pack.cu", "s2l_audio.cu", "s2l_mlp_fp32.cu", "s2l_mlp_tc.cu", "s2l_mlp_tc2.cu", "s2l_reduce.cu", "s2l_postfusion.cu", "s2l_mlp_bwd.cu"]
 LIB = os.path.join(HERE, "libs2l_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -32,171 +32,10 @@
 //
 // Warp roles (512 threads): w0 weight producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
 // w4-7 PE producers, w8-15 epilogue (two warps per TMEM lane quadrant, 32 columns each).
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <cuda_fp8.h>
-#include <cstdio>
-#include "s2l_common.cuh"
-#include "s2l_points.cuh"
+#include <cstdlib>
+#include "s2l_tc_common.cuh"
 
 namespace s2l {
-
-constexpr int TC_TM = 128;
-constexpr int TC_THREADS = 512;
-constexpr int NSTG = 9;
-constexpr int PE_PLANE = TC_TM * 128;              // 16 KB: [128 rows][64 K] bf16, SW128
-constexpr int PE_BUF = 2 * PE_PLANE;               // hi + lo
-constexpr int SM_PE = 0;                           // 2 buffers
-constexpr int SM_STG = SM_PE + 2 * PE_BUF;         // 65536
-constexpr int kStageBytes = kGranPlane;            // one plane per ring stage
-constexpr int SM_TCBIAS = SM_STG + NSTG * kStageBytes;
-constexpr int SM_FBIAS = SM_TCBIAS + kNumG * 256 * 4;
-constexpr int SM_BAR = SM_FBIAS + 2 * 2 * 256 * 4;
-constexpr int NBAR = 2 * NSTG + 2 + 2 + 4 + 4;
-constexpr int SM_TMEMPTR = SM_BAR + NBAR * 8;
-constexpr int TC_SMEM_BYTES = SM_TMEMPTR + 16;
-
-struct TcArgs {
-  const uint8_t* blob;
-  Layout L;
-  PointSrc src;
-  const float* frame_bias;   // [F,4,256]; rows 2,3 = folded bias0', bias5'
-  float* out;                // [F*P, out_ch]
-  int out_ch;
-  int n_frames;
-  long long tiles_per_frame;
-  long long* dbg;            // S2L_TIMELINE builds only: event log of CTA 0 (tools/tc_timeline.py)
-};
-
-// Cycle-stamped event log for pipeline analysis; compiled out unless -DS2L_TIMELINE.
-#ifdef S2L_TIMELINE
-#define TL(role, code) do { if (a.dbg && blockIdx.x == 0 && it == 2) { \
-    long long* _p = a.dbg + (role) * 2048; long long _n = _p[0]; if (_n < 1000) { _p[1 + 2 * _n] = (code); _p[2 + 2 * _n] = clock64(); _p[0] = _n + 1; } } } while (0)
-#else
-#define TL(role, code) do { } while (0)
-#endif
-
-// ------------------------------------------------------------------ tcgen05 wrappers
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (8-row atoms of 1024 B):
-// start>>4 | LBO=1 (unused for swizzled K-major) | SBO=1024>>4 | version=1 (sm_100) | layout=SWIZZLE_128B
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-// kind::f16 with fp16 operands / kind::f8f6f4 instruction descriptors (D = f32, K-major, M = 128, N = n)
-__host__ __device__ constexpr uint32_t idesc_f16(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__host__ __device__ constexpr uint32_t idesc_f8(int n, uint32_t a_fmt, uint32_t b_fmt) {   // 0 = e4m3, 1 = e5m2
-  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma8_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-
-// Bounded mbarrier wait: a protocol bug must surface as a trapped kernel, never as a hung GPU box.
-template <bool BACKOFF = false>
-__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (BACKOFF) __nanosleep(128);     // roles that run ahead (producers) must not steal issue slots while they wait
-    if (clock64() - t0 > 4000000000ll) {
-      printf("s2l tc kernel: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
-             threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);     // .x (low 16 bits) = lo, .y = hi
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);                // .x (low 16 bits) = lo
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// four floats -> four fp8 bytes, element i in byte i
-__device__ __forceinline__ uint32_t pack_fp8x4(float a, float b, float c, float d, __nv_fp8_interpretation_t kind) {
-  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, kind);
-  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, kind);
-  return lo | (hi << 16);
-}
 
 template <int NPASS, int UVD>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -602,6 +441,19 @@ static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   return check_launch("mlp_tc_kernel") ? 0 : 5;
 }
 
+int launch_mlp_tc2(const TcArgs& a, long long n_tiles, int npass, cudaStream_t st);   // s2l_mlp_tc2.cu (CTA pairs)
+
+// S2L_TC_IMPL=2 selects the CTA-pair (cta_group::2) kernel; the single-CTA kernel of this file is the default
+// (measured round 1, 4.19 M points: bf16x3 8.4 vs 8.4 ms, fp16f8 7.4 vs 8.4 ms, bf16x1 4.4 vs 5.6 ms).
+static int tc_impl() {
+  static int impl = 0;
+  if (impl == 0) {
+    const char* e = getenv("S2L_TC_IMPL");
+    impl = (e && e[0] == '2') ? 2 : 1;
+  }
+  return impl;
+}
+
 static long long* g_timeline = nullptr;
 extern "C" void s2l_debug_set_timeline(long long* buf) { g_timeline = buf; }     // debug builds (tools/tc_timeline.py)
 
@@ -619,6 +471,8 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   a.dbg = g_timeline;
   const long long n_tiles = a.tiles_per_frame * n_frames;
   if (n_tiles == 0) return 0;
+  if (src.uv_dims != 2 && src.uv_dims != 3) { set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims); return 2; }
+  if (tc_impl() == 2) return launch_mlp_tc2(a, n_tiles, npass, st);
   if (src.uv_dims == 2)
     return npass == 3 ? launch_tc_impl<3, 2>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 2>(a, n_tiles, st) : launch_tc_impl<1, 2>(a, n_tiles, st);
   if (src.uv_dims == 3)

@@ -461,3 +461,33 @@ def test_config4_512x512x128_properties(S):
     assert err < PARITY_TOL
     assert torch.isfinite(a[0]).all() and (a[1] >= 0).all() and (a[1].sum(-1) <= 1 + 1e-4).all()
     assert O.psnr(a[0].cpu(), b.cpu()) > 80.0
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel(S):
+    """the cta_group::2 implementation (S2L_TC_IMPL=2, s2l_mlp_tc2.cu) is an alternative schedule of the same
+    arithmetic: it must reproduce the default kernel within accumulation-order noise in every precision mode."""
+    import subprocess, sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import speech2lip_b200 as s2l
+from oracle import synth
+dev = torch.device("cuda:0")
+sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
+w = s2l.PackedWeights(sd)
+a = torch.from_numpy(synth.make_audio(3, seed=5)).to(dev)
+for prec in ("bf16x3", "fp16f8", "bf16x1"):
+    out = s2l.LipRenderer(w, prec).render_frames(a, torch.tensor([1, 2, 3]), 37, 53)
+    torch.save(out.cpu(), sys.argv[1] + prec + ".pt")
+""" % ROOT
+    import tempfile
+    outs = {}
+    for impl in ("1", "2"):
+        d = tempfile.mkdtemp()
+        env = dict(os.environ, S2L_TC_IMPL=impl)
+        subprocess.run([sys.executable, "-c", code, d + "/"], check=True, env=env, timeout=600)
+        outs[impl] = {p: torch.load(d + "/" + p + ".pt") for p in ("bf16x3", "fp16f8", "bf16x1")}
+    for p in ("bf16x3", "fp16f8", "bf16x1"):
+        err = (outs["1"][p] - outs["2"][p]).abs().max().item()
+        print("impl 1 vs 2 %s maxabs %.3e" % (p, err))
+        assert err < 2e-5
