@@ -80,6 +80,9 @@ typedef struct S2LGeom {
                                            0 -> [F*R,3]                                       */
   int64_t pts_per_frame;   /* EXPLICIT: P (points per frame); otherwise derived               */
   float   eps_shift;       /* GRID_ENS4: the reference's eps_shift draw (training.py:200)     */
+  const float* eps_per_frame; /* GRID_ENS4, optional DEVICE array [F]: one draw per frame (the sync-window
+                                 render calls predict_lip_image once per frame, training.py:504-525);
+                                 NULL -> eps_shift is used for every frame                             */
 } S2LGeom;
 
 /* Thread-local description of the last error (never NULL). */
@@ -176,6 +179,15 @@ int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* face_canonica
                                 int32_t lip_w, int32_t face_h, int32_t face_w, int32_t out_h, int32_t out_w,
                                 int32_t lefttop_x, int32_t lefttop_y, int32_t paste_shift, int32_t expand_pad,
                                 float* fused_nchw, float* merged_canonical, void* stream);
+
+/* Replaces: the windowing of preprocess/deepspeech_features/deepspeech_features.py:65-75 (zero-pad 8 rows on both
+ * sides, 16-row windows, stride 2): logits [T,29] -> windows [ceil(T/2),16,29]  (the hot path's input format). */
+int32_t s2l_audio_windows(const float* logits, int64_t n_steps, float* windows, void* stream);
+
+/* Replaces: the output staging of inference.py:173-178 (cv2.cvtColor RGB2BGR + cv2.imwrite(path, img * 255), i.e.
+ * x*255 in fp32, round-half-even, saturate to [0,255], channel swap): rgb [N_pixels,3] fp32 -> bgr [N_pixels,3] u8.
+ * Cuts the device->host bytes of a finished frame 4x. */
+int32_t s2l_frames_to_bgr8(const float* rgb, int64_t n_pixels, uint8_t* bgr, void* stream);
 
 /* Number of kernels of this library launched by this thread since the last reset (bench "gpu_launches"). */
 int64_t s2l_launch_count(int32_t reset);

@@ -247,6 +247,26 @@ def post_fusion_compose(rgb_lip, rgb_face_canonical, rgb_gt, mask_lip_canonical,
     return out.permute(0, 2, 3, 1), canon
 
 
+def audio_windows(logits):
+    """preprocess/deepspeech_features/deepspeech_features.py:65-75: zero-pad win_size/2 rows on both sides, then
+    16-row windows with stride 2.  logits [T,29] (numpy or tensor) -> float32 tensor [ceil(T/2),16,29]."""
+    x = np.asarray(logits, dtype=np.float64).reshape(-1, 29)
+    win_size = 16
+    zero_pad = np.zeros((int(win_size / 2), x.shape[1]))
+    x = np.concatenate((zero_pad, x, zero_pad), axis=0)
+    windows = [x[i:i + win_size] for i in range(0, x.shape[0] - win_size, 2)]
+    return torch.from_numpy(np.array(windows).astype(np.float32).reshape(-1, 16, 29))
+
+
+def frames_to_bgr8(rgb):
+    """inference.py:173-178: cv2.cvtColor(img, COLOR_RGB2BGR); cv2.imwrite(path, img * 255).  imwrite converts the
+    float image with Mat::convertTo(CV_8U) = saturate_cast<uchar>(cvRound(v)): round-half-even, clamp, NaN -> 0."""
+    v = np.asarray(rgb, dtype=np.float32) * np.float32(255.0)
+    r = np.rint(v)
+    r = np.where(np.isnan(r), 0.0, r)
+    return torch.from_numpy(np.clip(r, 0, 255).astype(np.uint8)[..., ::-1].copy())
+
+
 def psnr(a, b, peak=1.0):
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     if mse == 0:

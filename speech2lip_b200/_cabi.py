@@ -30,7 +30,8 @@ assert len(PARAM_NAMES) == NUM_PARAMS
 class S2LGeom(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_samples", C.c_int32),
                 ("pts_mode", C.c_int32), ("uv_dims", C.c_int32), ("out_ch", C.c_int32), ("z_per_ray", C.c_int32),
-                ("rays_per_frame_shared", C.c_int32), ("pts_per_frame", C.c_int64), ("eps_shift", C.c_float)]
+                ("rays_per_frame_shared", C.c_int32), ("pts_per_frame", C.c_int64), ("eps_shift", C.c_float),
+                ("eps_per_frame", C.c_void_p)]
 
 
 SYMBOLS = {
@@ -57,6 +58,8 @@ SYMBOLS = {
     "s2l_render_frames": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "s2l_post_fusion_compose": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p] * 3),
+    "s2l_audio_windows": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "s2l_frames_to_bgr8": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "s2l_launch_count": (C.c_int64, [C.c_int32]),
 }
 

@@ -75,6 +75,7 @@ static PointSrc make_src(const S2LGeom& g, const float* pts, const float* ro, co
   s.z_per_ray = g.z_per_ray;
   s.rays_shared = g.rays_per_frame_shared;
   s.eps = g.eps_shift;
+  s.eps_pf = (g.pts_mode == S2L_PTS_GRID_ENS4) ? g.eps_per_frame : nullptr;
   s.P = points_per_frame(g);
   s.pts = pts;
   s.rays_o = ro;

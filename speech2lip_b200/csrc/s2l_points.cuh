@@ -12,6 +12,7 @@ struct PointSrc {
   int z_per_ray;
   int rays_shared;
   float eps;            // GRID_ENS4 eps_shift
+  const float* eps_pf;  // optional per-frame eps_shift [F]
   long long P;          // point evaluations per frame
   const float* pts;     // EXPLICIT: [F*P, uv_dims]
   const float* rays_o;  // RAYS
@@ -39,8 +40,9 @@ __device__ __forceinline__ void gen_point(const PointSrc& s, int f, long long p,
     const float vx = (tap & 2) ? 1.f : -1.f, vy = (tap & 1) ? 1.f : -1.f;
     const float rx = (float)((double)vx * (0.5 / (double)s.W));
     const float ry = (float)((double)vy * (0.5 / (double)s.H));
-    const float u = __fadd_rn(linspace01(px, s.W), __fadd_rn(rx, s.eps));
-    const float v = __fadd_rn(linspace01(py, s.H), __fadd_rn(ry, s.eps));
+    const float eps = s.eps_pf ? s.eps_pf[f] : s.eps;
+    const float u = __fadd_rn(linspace01(px, s.W), __fadd_rn(rx, eps));
+    const float v = __fadd_rn(linspace01(py, s.H), __fadd_rn(ry, eps));
     x[0] = fminf(fmaxf(u, 0.f), 1.f);
     x[1] = fminf(fmaxf(v, 0.f), 1.f);
   } else if (s.mode == S2L_PTS_RAYS) {

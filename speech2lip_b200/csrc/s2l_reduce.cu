@@ -116,9 +116,54 @@ __global__ void get_rays_kernel(const float* __restrict__ c2w, int H, int W, flo
   }
 }
 
+// deepspeech_features.py:65-75: zero-pad 8 rows each side, windows of 16 rows with stride 2
+__global__ void audio_windows_kernel(const float* __restrict__ logits, long long T, float* __restrict__ win) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nw = (T + 1) / 2;
+  if (gid >= nw * 16 * 29) return;
+  const int c = (int)(gid % 29);
+  const int r = (int)((gid / 29) % 16);
+  const long long w = gid / (29 * 16);
+  const long long src = 2 * w + r - 8;
+  win[gid] = (src >= 0 && src < T) ? logits[src * 29 + c] : 0.f;
+}
+
+// inference.py:173-178: cvtColor(RGB2BGR) then imwrite(img * 255): fp32 multiply, cvRound (half-to-even), saturate
+__global__ void frames_to_bgr8_kernel(const float* __restrict__ rgb, long long n, uint8_t* __restrict__ bgr) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n) return;
+  const float* p = rgb + gid * 3;
+  uint8_t o[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = rintf(__fmul_rn(p[c], 255.f));
+    o[2 - c] = (uint8_t)(v >= 255.f ? 255 : (v > 0.f ? (int)v : 0));      // NaN -> 0 like cv::saturate_cast
+  }
+  bgr[gid * 3 + 0] = o[0];
+  bgr[gid * 3 + 1] = o[1];
+  bgr[gid * 3 + 2] = o[2];
+}
+
 }  // namespace s2l
 
 using namespace s2l;
+
+extern "C" int32_t s2l_audio_windows(const float* logits, int64_t n_steps, float* windows, void* stream) {
+  if (n_steps < 0) { set_error("s2l_audio_windows: negative n_steps"); return 2; }
+  if (n_steps == 0) return 0;
+  if (!logits || !windows) { set_error("s2l_audio_windows: null argument"); return 1; }
+  const long long n = ((long long)n_steps + 1) / 2 * 16 * 29;
+  audio_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, n_steps, windows);
+  return check_launch("audio_windows_kernel") ? 0 : 5;
+}
+
+extern "C" int32_t s2l_frames_to_bgr8(const float* rgb, int64_t n_pixels, uint8_t* bgr, void* stream) {
+  if (n_pixels < 0) { set_error("s2l_frames_to_bgr8: negative n_pixels"); return 2; }
+  if (n_pixels == 0) return 0;
+  if (!rgb || !bgr) { set_error("s2l_frames_to_bgr8: null argument"); return 1; }
+  frames_to_bgr8_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rgb, n_pixels, bgr);
+  return check_launch("frames_to_bgr8_kernel") ? 0 : 5;
+}
 
 extern "C" int32_t s2l_ensemble4_blend(const float* raw, const S2LGeom* g, float* rgb, void* stream) {
   if (!raw || !g || !rgb) { set_error("s2l_ensemble4_blend: null argument"); return 1; }
@@ -128,6 +173,7 @@ extern "C" int32_t s2l_ensemble4_blend(const float* raw, const S2LGeom* g, float
   src.W = g->width;
   src.uv_dims = 2;
   src.eps = g->eps_shift;
+  src.eps_pf = g->eps_per_frame;
   src.P = (long long)g->height * g->width * 4;
   const long long n = (long long)g->height * g->width * g->n_frames;
   if (n == 0) return 0;

@@ -184,6 +184,29 @@ def post_fusion_compose(rgb_lip, face_canonical, rgb_gt, mask_lip_canonical, coo
     return fused, canon
 
 
+def audio_windows(logits):
+    """deepspeech_features.py:65-75: DeepSpeech logits [T,29] -> 16-step windows with stride 2, [ceil(T/2),16,29]."""
+    lib = _cabi.lib()
+    x = _f32c(logits, "logits").reshape(-1, 29)
+    T = x.shape[0]
+    out = torch.empty((T + 1) // 2, 16, 29, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_audio_windows(_ptr(x), T, _ptr(out), _stream()), "s2l_audio_windows")
+    return out
+
+
+def frames_to_bgr8(rgb):
+    """inference.py:173-178 output staging: [...,3] fp32 RGB -> uint8 BGR exactly as cv2.imwrite(img * 255) stores it."""
+    lib = _cabi.lib()
+    x = _f32c(rgb, "rgb")
+    if x.shape[-1] != 3:
+        raise ValueError("rgb must have 3 channels last")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_frames_to_bgr8(_ptr(x), x.numel() // 3, _ptr(out), _stream()), "s2l_frames_to_bgr8")
+    return out
+
+
 class LipRenderer:
     """Batched frame renderer over one PackedWeights blob.
 
@@ -220,8 +243,15 @@ class LipRenderer:
         if idx.numel() != F:
             raise ValueError("index has %d entries for %d frames" % (idx.numel(), F))
         prec = _cabi.PRECISIONS[precision or self.precision]
+        eps_pf = None
+        if isinstance(eps_shift, torch.Tensor) and eps_shift.numel() > 1:      # one draw per frame (sync-window render)
+            eps_pf = eps_shift.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            if eps_pf.numel() != F:
+                raise ValueError("eps_shift has %d entries for %d frames" % (eps_pf.numel(), F))
+            eps_shift = 0.0
         g = S2LGeom(n_frames=F, height=H, width=W, n_samples=0, pts_mode=_cabi.PTS_GRID, uv_dims=self.w.uv_dims,
-                    out_ch=self.w.out_ch, z_per_ray=0, rays_per_frame_shared=0, pts_per_frame=0, eps_shift=float(eps_shift))
+                    out_ch=self.w.out_ch, z_per_ray=0, rays_per_frame_shared=0, pts_per_frame=0, eps_shift=float(eps_shift),
+                    eps_per_frame=None if eps_pf is None else eps_pf.data_ptr())
         weights = depth = None
         if mode == "plain":
             g.pts_mode = _cabi.PTS_GRID
@@ -275,6 +305,14 @@ class LipRenderer:
         if return_aux:
             return out, weights, depth
         return out
+
+    def render_sync_window(self, audio_window, index, total_frame, H, W, eps_shift):
+        """The sync-expert loss window (training.py:500-525): T consecutive lip frames, each through the 4-tap
+        ensemble with its own audio window, time index min(index + t, total_frame - 1) and its own eps_shift draw —
+        ONE launch instead of T predict_lip_image calls.  audio_window [T,16,29], eps_shift [T] -> [T,H,W,3]."""
+        T = audio_window.shape[0]
+        idx = torch.clamp(torch.arange(T, device=audio_window.device) + int(index), max=int(total_frame) - 1)
+        return self.render_frames(audio_window, idx, H, W, mode="ensemble4", eps_shift=torch.as_tensor(eps_shift))
 
     def render_frames_host(self, audio_host, index_host, H, W, out_host=None, **kw):
         """End-to-end call on HOST buffers: H2D of the audio windows / indices (pinned -> async), render,

@@ -165,6 +165,33 @@ def main_postfusion():
     np.savez_compressed(os.path.join(OUT, "reference_golden_postfusion.npz"), **flat)
 
 
+def main_staging():
+    """tests/golden/reference_golden_staging.npz: (a) the windowing lines of deepspeech_features.py:65-75 run verbatim
+    on random logits, (b) cv2.cvtColor + cv2.imwrite(img * 255) (inference.py:173-178) through a lossless PNG."""
+    import cv2
+    import tempfile
+    rng = np.random.Generator(np.random.PCG64(77))
+    x = rng.uniform(-0.2, 1.2, size=(37, 53, 3)).astype(np.float32)
+    x[0, 0] = [0.5 / 255, 1.5 / 255, 2.5 / 255]
+    x[0, 1] = [254.5 / 255, 0.49999 / 255, np.nan]
+    x[0, 2] = [1.0, 0.0, -0.0]
+    bgr = cv2.cvtColor(x, cv2.COLOR_RGB2BGR)
+    path = os.path.join(tempfile.mkdtemp(), "t.png")
+    cv2.imwrite(path, bgr * 255)
+    u8 = cv2.imread(path, cv2.IMREAD_COLOR)
+    logits = rng.normal(size=(23, 29)).astype(np.float32)
+    net_output = logits.reshape(-1, 29)
+    win_size = 16
+    zero_pad = np.zeros((int(win_size / 2), net_output.shape[1]))
+    net_output = np.concatenate((zero_pad, net_output, zero_pad), axis=0)
+    windows = []
+    for window_index in range(0, net_output.shape[0] - win_size, 2):
+        windows.append(net_output[window_index:window_index + win_size])
+    np.savez_compressed(os.path.join(OUT, "reference_golden_staging.npz"),
+                        **{"u8/rgb": x, "u8/bgr8": u8, "win/logits": logits, "win/windows": np.array(windows).astype(np.float32)})
+
+
 if __name__ == "__main__":
     main()
     main_postfusion()
+    main_staging()

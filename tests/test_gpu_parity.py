@@ -491,3 +491,38 @@ for prec in ("bf16x3", "fp16f8", "bf16x1"):
         err = (outs["1"][p] - outs["2"][p]).abs().max().item()
         print("impl 1 vs 2 %s maxabs %.3e" % (p, err))
         assert err < 2e-5
+
+
+# ------------------------------------------------------------------------------------------ next rows 3 and 4
+def test_staging_kernels_vs_golden(S, golden):
+    """DeepSpeech windowing and the uint8 BGR output staging, bit-exact against the reference's
+    numpy lines / real cv2."""
+    w = golden["win"]
+    got = S.audio_windows(torch.from_numpy(w["logits"]).to(dev()))
+    assert torch.equal(got.cpu(), torch.from_numpy(w["windows"]))
+    assert S.audio_windows(torch.zeros(0, 29, device=dev())).shape == (0, 16, 29)
+    odd = S.audio_windows(torch.randn(1, 29, device=dev()))
+    assert odd.shape == (1, 16, 29) and torch.equal(odd[0, :8], torch.zeros(8, 29, device=dev()))
+    u = golden["u8"]
+    b = S.frames_to_bgr8(torch.from_numpy(u["rgb"]).to(dev()))
+    assert b.dtype == torch.uint8 and torch.equal(b.cpu(), torch.from_numpy(u["bgr8"]))
+    big = torch.rand(4, 256, 256, 3, device=dev())
+    assert torch.equal(S.frames_to_bgr8(big).cpu(), O.frames_to_bgr8(big.cpu().numpy()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16f8"])
+def test_sync_window_render_vs_oracle(S, precision):
+    """the 5-frame sync-loss window (training.py:500-525) in ONE launch: per-frame audio window,
+    index clamped to total_frame-1, per-frame eps_shift draw."""
+    H, W, T = 20, 30, 5
+    aw = torch.from_numpy(synth.make_audio(T, seed=31))
+    eps = (0.5 / H) * torch.rand(T, generator=torch.Generator().manual_seed(3)) / 2.0
+    index, total = 97, 100                                  # frames 97, 98, 99, 99, 99
+    sd = osd("trained")
+    want = torch.stack([O.render_ensemble4(sd, aw[t:t + 1], min(index + t, total - 1), H, W, eps[t]) for t in range(T)])
+    r = S.LipRenderer(packed(S, "trained"), precision)
+    got = r.render_sync_window(aw.to(dev()), index, total, H, W, eps).cpu()
+    err = maxabs(got, want)
+    print("sync window %s maxabs %.3e" % (precision, err))
+    assert err < (3e-4 if precision == "fp32" else PARITY_TOL)
+    assert not torch.equal(got[3], got[4])                  # same index, different audio window and eps

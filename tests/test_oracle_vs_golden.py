@@ -118,3 +118,13 @@ def test_post_fusion_compose(golden, case):
         _, fused2, canon2 = m.post_fusion2_onlylip(t("lip"), t("face"), t("gt"), t("mask"), int(g["x0"]), int(g["y0"]), t("coord"))
     np.testing.assert_allclose(fused2.numpy(), g["fused"], atol=1e-7, rtol=0)
     np.testing.assert_array_equal(canon2.numpy(), g["canon"])
+
+
+def test_staging_formats(golden):
+    """the wire formats either side of the path — DeepSpeech windowing (golden = the reference's
+    numpy lines run verbatim) and the uint8 BGR frame cv2.imwrite stores (golden = real cv2 round trip through PNG)."""
+    w = golden["win"]
+    np.testing.assert_array_equal(O.audio_windows(w["logits"]).numpy(), w["windows"])
+    assert w["windows"].shape == (12, 16, 29)
+    u = golden["u8"]
+    np.testing.assert_array_equal(O.frames_to_bgr8(u["rgb"]).numpy(), u["bgr8"])
