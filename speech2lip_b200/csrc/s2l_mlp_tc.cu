@@ -37,26 +37,38 @@
 
 namespace s2l {
 
+// shared-memory map of this kernel: PE images (2 x 32 KB) | 4-stage ring of 32 KB granules | biases | barriers
+constexpr int T1_NSTG = 4;                          // power of two
+constexpr int T1_STAGE = kGranBytes;                // 32 KB: both planes of a granule
+constexpr int T1_SM_TCBIAS = SM_STG + T1_NSTG * T1_STAGE;
+constexpr int T1_SM_FBIAS = T1_SM_TCBIAS + kNumG * 256 * 4;
+constexpr int T1_SM_BAR = T1_SM_FBIAS + 2 * 2 * 256 * 4;
+constexpr int T1_NBAR = 2 * T1_NSTG + 2 + 2 + 4 + 4;
+constexpr int T1_SM_TMEMPTR = T1_SM_BAR + T1_NBAR * 8;
+constexpr int T1_SMEM_BYTES = T1_SM_TMEMPTR + 16;
+static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
+
 template <int NPASS, int UVD>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T1_SM_BAR);
   uint64_t* b_full = bars;
-  uint64_t* b_empty = bars + NSTG;
-  uint64_t* pe_full = bars + 2 * NSTG;
+  uint64_t* b_empty = bars + T1_NSTG;
+  uint64_t* pe_full = bars + 2 * T1_NSTG;
   uint64_t* pe_empty = pe_full + 2;
   uint64_t* acc_full = pe_empty + 2;
   uint64_t* epi_done = acc_full + 4;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_TMEMPTR);
-  float* tcbias_s = reinterpret_cast<float*>(smem + SM_TCBIAS);
-  float* fbias_s = reinterpret_cast<float*>(smem + SM_FBIAS);   // [2 bufs][2][256]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + T1_SM_TMEMPTR);
+  float* tcbias_s = reinterpret_cast<float*>(smem + T1_SM_TCBIAS);
+  float* fbias_s = reinterpret_cast<float*>(smem + T1_SM_FBIAS);   // [2 bufs][2][256]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches and the MMA warp's loop state stay on the uniform datapath
   const long long n_tiles = a.tiles_per_frame * a.n_frames;
   const uint8_t* tcw = a.blob + (NPASS == 2 ? a.L.off_tcw8 : a.L.off_tcw);
 
   if (tid == 0) {
-    for (int s = 0; s < NSTG; ++s) {
+    for (int s = 0; s < T1_NSTG; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
@@ -82,141 +94,143 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
   if (warp == 0) {
     // =============================================================== weight producer
+    // One stage = one granule (both planes of a [128 N x 64 K] weight tile, contiguous in the blob) = ONE bulk copy.
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int g = 0; g < kNumG; ++g) {
           const int ngran = (g == 8) ? 4 : 2 * g_nkc(g);
-          const uint32_t plane = (g == 8) ? kOutPlane : kGranPlane;
+          const uint32_t gran = (g == 8) ? kOutGranBytes : kGranBytes;
+          const uint32_t bytes = (NPASS == 1) ? gran / 2 : gran;        // bf16x1 only needs the hi plane
           const uint8_t* src = tcw + g_layer_off(g);
 #pragma unroll 1
-          for (int pi = 0; pi < ngran * 2; ++pi) {           // planes in issue order: hi(gi), lo(gi), hi(gi+1), ...
-            if (NPASS == 1 && (pi & 1)) continue;
+          for (int gi = 0; gi < ngran; ++gi) {
             mbar_wait_wd<true>(&b_empty[stage], phase ^ 1u, 100 + stage);
-            mbar_arrive_expect_tx(&b_full[stage], plane);
-            bulk_g2s(smem + SM_STG + stage * kStageBytes, src + (size_t)pi * plane, plane, &b_full[stage]);
-            if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+#ifdef S2L_DBG_NOLOAD        // experiment: weights are never streamed (results are garbage, timing only)
+            mbar_arrive(&b_full[stage]);
+#else
+            mbar_arrive_expect_tx(&b_full[stage], bytes);
+            bulk_g2s(smem + SM_STG + stage * T1_STAGE, src + (size_t)gi * gran, bytes, &b_full[stage]);
+#endif
+            stage = (stage + 1) & (T1_NSTG - 1);
+            phase ^= (stage == 0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================================================== MMA issuer (one thread)
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t epi_par = 0;                       // bit hk = parity to wait for on epi_done[hk]
-      int rp = 0;
-      long long it = 0;
-      constexpr uint32_t kDescHi = 0x40004040u;   // SBO=64 | version=1 | SWIZZLE_128B  (upper descriptor word)
-      auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi << 32) | lo; };
-      constexpr uint32_t kDescHi64 = 0x80004020u; // SBO=32 (512 B atoms) | version=1 | SWIZZLE_64B: 8-bit operands, 64 K per row
-      auto mk64 = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi64 << 32) | lo; };
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = (int)(it & 1);
-        const uint32_t pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
-        const uint32_t pe_lo = pe_hi + (PE_PLANE >> 4);
-        const uint32_t pe_e5 = pe_lo, pe_e4 = pe_lo + (PE_PLANE >> 5);      // NPASS == 2: [fp16 16 KB | e5m2 8 KB | e4m3 8 KB]
+    // =============================================================== MMA issuer
+    // The whole warp walks the layer program in lock step (so every address / descriptor below is computed on the
+    // uniform datapath, off the critical path); one elected lane issues the tcgen05 instructions of a granule
+    // back to back: one barrier wait and one commit per 8-12 MMAs.
+    uint32_t stage = 0, phase = 0;
+    uint32_t epi_par = 0;                       // bit hk = parity to wait for on epi_done[hk]
+    int rp = 0;
+    long long it = 0;
+    TL_DECL;
+    constexpr uint32_t kDescHi = 0x40004040u;   // SBO=64 | version=1 | SWIZZLE_128B  (upper descriptor word)
+    auto mk = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi << 32) | lo; };
+    constexpr uint32_t kDescHi64 = 0x80004020u; // SBO=32 (512 B atoms) | version=1 | SWIZZLE_64B: 8-bit operands, 64 K per row
+    auto mk64 = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi64 << 32) | lo; };
+    const uint32_t stg0 = ((smem_u32(smem + SM_STG) >> 4) & 0x3FFFu) | 0x10000u;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
+      const uint32_t pe_lo = pe_hi + (PE_PLANE >> 4);
+      const uint32_t pe_e5 = pe_lo, pe_e4 = pe_lo + (PE_PLANE >> 5);      // NPASS == 2: [fp16 16 KB | e5m2 8 KB | e4m3 8 KB]
 #pragma unroll 1
-        for (int g = 0; g < kNumG; ++g) {
-          const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
-          const uint32_t a_region = tmem_base + (rp ? 0u : 256u);
-          const int nh = (g == 8) ? 1 : 2;
-          const int n_mma = (g == 8) ? kOutPad : kGranRows;
-          const uint32_t idesc = (NPASS == 2) ? idesc_f16(n_mma) : idesc_bf16(n_mma);
-          const uint32_t idesc_rw = idesc_f8(n_mma, 0u, 1u);     // (A - fp16 A) [e4m3] x fp16(W) [e5m2]
-          const uint32_t idesc_wr = idesc_f8(n_mma, 1u, 0u);     // fp16(A) [e5m2] x (W - fp16 W) [e4m3]
-          const int nkc = g_nkc(g);
+      for (int g = 0; g < kNumG; ++g) {
+        const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
+        const uint32_t a_region = tmem_base + (rp ? 0u : 256u);
+        const int nh = (g == 8) ? 1 : 2;
+        const int n_mma = (g == 8) ? kOutPad : kGranRows;
+        const uint32_t idesc = (NPASS == 2) ? idesc_f16(n_mma) : idesc_bf16(n_mma);
+        const uint32_t idesc_rw = idesc_f8(n_mma, 0u, 1u);     // (A - fp16 A) [e4m3] x fp16(W) [e5m2]
+        const uint32_t idesc_wr = idesc_f8(n_mma, 1u, 0u);     // fp16(A) [e5m2] x (W - fp16 W) [e4m3]
+        const uint32_t plane16 = (uint32_t)(((g == 8) ? kOutPlane : kGranPlane) >> 4);   // second plane of the granule
+        const int nkc = g_nkc(g);
+        if (g == 0) mbar_wait_trap(&pe_full[buf], (uint32_t)((it >> 1) & 1));
 #pragma unroll 1
-          for (int h = 0; h < nh; ++h) {
-            const uint32_t d_addr = d_region + (uint32_t)h * 128u;
-            TL(0, 1000 + g * 10 + h);                       // MMA thread starts half h of layer g
+        for (int h = 0; h < nh; ++h) {
+          const uint32_t d_addr = d_region + (uint32_t)h * 128u;
+          TL(0, 1000 + g * 10 + h);                       // MMA warp starts half h of layer g
 #pragma unroll 1
-            for (int kc = 0; kc < nkc; ++kc) {
-              const bool is_pe = (g == 0) || (g == 5 && kc == 0);
-              const int hk = (g == 5) ? kc - 1 : kc;
-              if (h == 0) {
-                if (g == 0) mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 200 + buf);
-                if (!is_pe) {
-                  mbar_wait_wd(&epi_done[hk], (epi_par >> hk) & 1u, 300 + hk);
-                  epi_par ^= 1u << hk;
+          for (int kc = 0; kc < nkc; ++kc) {
+            const bool is_pe = (g == 0) || (g == 5 && kc == 0);
+            const int hk = (g == 5) ? kc - 1 : kc;
+            TLC(0);
+            if (h == 0 && !is_pe) {
+              mbar_wait_trap(&epi_done[hk], (epi_par >> hk) & 1u);
+              epi_par ^= 1u << hk;
+            }
+            TLC(1);
+            mbar_wait_trap(&b_full[stage], phase);
+            TLC(2);
+            tc_fence_after();
+            // A chunk layout in TMEM (64 cols): bf16: [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
+            //                                   fp16f8, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
+            const uint32_t a_t = a_region + (uint32_t)hk * 64u;
+            const uint32_t b = stg0 + stage * (uint32_t)(T1_STAGE >> 4);      // first plane: hi / fp16
+            const uint32_t b2 = b + plane16;                                  // second plane: lo / [e5m2 | e4m3]
+            const uint32_t acc0 = (kc == 0) ? 0u : 1u;
+            if (elect_one()) {
+              if (is_pe) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                  umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, s == 0 ? acc0 : 1u);
+                  if (NPASS == 3) umma_ss(d_addr, mk(pe_lo + 2 * s), mk(b + 2 * s), idesc, 1u);
                 }
-              }
-              // A chunk layout in TMEM (64 cols): [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
-              const uint32_t a_t = a_region + (uint32_t)hk * 64u;
-              // ---- hi weight plane: A_hi*W_hi (+ A_lo*W_hi)
-              mbar_wait_wd(&b_full[stage], phase, 400 + stage);
-              tc_fence_after();
-              {
-                const uint32_t b = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
-                if (is_pe) {
+                if (NPASS == 3) {
 #pragma unroll
-                  for (int s = 0; s < 4; ++s) {
-                    umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, (kc == 0 && s == 0) ? 0u : 1u);
-                    if (NPASS == 3) umma_ss(d_addr, mk(pe_lo + 2 * s), mk(b + 2 * s), idesc, 1u);
-                  }
-                } else {
+                  for (int s = 0; s < 4; ++s) umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b2 + 2 * s), idesc, 1u);
+                }
+                if (NPASS == 2) {
+                  const uint32_t b4 = b2 + (plane16 >> 1);
 #pragma unroll
-                  for (int s = 0; s < 4; ++s) {
-                    const uint32_t a_hi = a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8);
-                    umma_ts(d_addr, a_hi, mk(b + 2 * s), idesc, (kc == 0 && s == 0) ? 0u : 1u);
-                    if (NPASS == 3) umma_ts(d_addr, a_hi + 16u, mk(b + 2 * s), idesc, 1u);
-                  }
+                  for (int t = 0; t < 2; ++t) umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b2 + 2 * t), idesc_rw, 1u);
+#pragma unroll
+                  for (int t = 0; t < 2; ++t) umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                  const uint32_t a_hi = a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8);
+                  umma_ts(d_addr, a_hi, mk(b + 2 * s), idesc, s == 0 ? acc0 : 1u);
+                  if (NPASS == 3) umma_ts(d_addr, a_hi + 16u, mk(b + 2 * s), idesc, 1u);
+                }
+                if (NPASS == 3) {
+#pragma unroll
+                  for (int s = 0; s < 4; ++s)
+                    umma_ts(d_addr, a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8), mk(b2 + 2 * s), idesc, 1u);
+                }
+                if (NPASS == 2) {
+                  const uint32_t b4 = b2 + (plane16 >> 1);
+                  // same-format MMAs are issued back to back (operand formats live in the instruction descriptor)
+#pragma unroll
+                  for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b2 + 2 * t), idesc_rw, 1u);
+#pragma unroll
+                  for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
                 }
               }
               umma_commit(&b_empty[stage]);      // stage reusable once these MMAs retire
-              if (++stage == NSTG) { stage = 0; phase ^= 1u; }
-              // ---- fp8 correction plane: [e5m2 fp16(W)*2^-8 | e4m3 (W-fp16 W)*2^10], two K=32 steps per 64-K chunk
-              if (NPASS == 2) {
-                mbar_wait_wd(&b_full[stage], phase, 450 + stage);
-                tc_fence_after();
-                const int plane8 = ((g == 8) ? kOutPlane : kGranPlane) / 2;
-                const uint32_t b5 = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
-                const uint32_t b4 = b5 + (uint32_t)(plane8 >> 4);
-                // same-format MMAs are issued back to back (operand formats live in the instruction descriptor)
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                  if (is_pe) umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b5 + 2 * t), idesc_rw, 1u);
-                  // A chunk layout in TMEM for this mode, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
-                  else umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b5 + 2 * t), idesc_rw, 1u);
-                }
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                  if (is_pe) umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
-                  else umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
-                }
-                umma_commit(&b_empty[stage]);
-                if (++stage == NSTG) { stage = 0; phase ^= 1u; }
-              }
-              // ---- lo weight plane: A_hi*W_lo
-              if (NPASS == 3) {
-                mbar_wait_wd(&b_full[stage], phase, 450 + stage);
-                tc_fence_after();
-                const uint32_t b = ((smem_u32(smem + SM_STG + stage * kStageBytes) >> 4) & 0x3FFFu) | 0x10000u;
-                if (is_pe) {
-#pragma unroll
-                  for (int s = 0; s < 4; ++s) umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, 1u);
-                } else {
-#pragma unroll
-                  for (int s = 0; s < 4; ++s)
-                    umma_ts(d_addr, a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8), mk(b + 2 * s), idesc, 1u);
-                }
-                umma_commit(&b_empty[stage]);
-                if (++stage == NSTG) { stage = 0; phase ^= 1u; }
+              if (kc == nkc - 1) {
+                umma_commit(&acc_full[h]);       // accumulator half h of layer g complete
+                if (g == 5 && h == 1) umma_commit(&pe_empty[buf]);   // last reader of this tile's PE image
               }
             }
-            umma_commit(&acc_full[h]);           // accumulator half h of layer g complete
-            TL(0, 5000 + g * 10 + h);
+            __syncwarp();
+            stage = (stage + 1) & (T1_NSTG - 1);
+            phase ^= (stage == 0);
           }
-          if (g == 5) umma_commit(&pe_empty[buf]);   // last reader of this tile's PE image
-          rp ^= 1;
+          TL(0, 5000 + g * 10 + h);
+          TLC_FLUSH(0);
         }
+        rp ^= 1;
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -316,6 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint32_t acc_par[4] = {0, 0, 0, 0};
     int rp = 0;
     long long it = 0;
+    TL_DECL;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
       const int f = (int)(tile / a.tiles_per_frame);
@@ -334,6 +349,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           // first quarter's conversion; each quarter is released to the MMA thread as soon as it is stored
           const uint32_t taddr0 = d_region + lane_sel + (uint32_t)(hh * 128 + half * 32);
           uint32_t va[32], vb[32];
+#ifdef S2L_DBG_NOEPI         // experiment: the epilogue only keeps the barrier protocol alive
+          for (int qq = 0; qq < 2; ++qq) { tc_fence_before(); mbar_arrive(&epi_done[hh * 2 + qq]); }
+          continue;
+#endif
           tmem_ld32(taddr0, va);
           tmem_ld32(taddr0 + 64u, vb);
           tmem_ld_wait();
@@ -427,8 +446,8 @@ static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   cudaGetDevice(&cur_dev);
   bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
-    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
-      set_error("mlp_tc: cannot opt in to %d B of shared memory: %s", TC_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
+    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM_BYTES) != cudaSuccess) {
+      set_error("mlp_tc: cannot opt in to %d B of shared memory: %s", T1_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
       return 6;
     }
     attr_set = true;
@@ -437,7 +456,7 @@ static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  mlp_tc_kernel<NPASS, UVD><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(a);
+  mlp_tc_kernel<NPASS, UVD><<<grid, TC_THREADS, T1_SMEM_BYTES, st>>>(a);
   return check_launch("mlp_tc_kernel") ? 0 : 5;
 }
 

@@ -40,9 +40,18 @@ struct TcArgs {
 
 // Cycle-stamped event log for pipeline analysis; compiled out unless -DS2L_TIMELINE.
 #ifdef S2L_TIMELINE
-#define TL(role, code) do { if (a.dbg && blockIdx.x == 0 && it == 2) { \
-    long long* _p = a.dbg + (role) * 2048; long long _n = _p[0]; if (_n < 1000) { _p[1 + 2 * _n] = (code); _p[2 + 2 * _n] = clock64(); _p[0] = _n + 1; } } } while (0)
+#define TL_DECL int tl_n = 0; long long tlc_t[3] = {0, 0, 0}, tlc_acc[2] = {0, 0}
+// cheap wait accounting: TLC(i) stamps a register; TLC_FLUSH logs (epilogue-wait, weight-wait) cycles of the half as codes 2xxx/3xxx
+#define TLC(i) do { tlc_t[i] = clock64(); if ((i) == 1) tlc_acc[0] += tlc_t[1] - tlc_t[0]; if ((i) == 2) tlc_acc[1] += tlc_t[2] - tlc_t[1]; } while (0)
+#define TLC_FLUSH(role) do { if (a.dbg && blockIdx.x == 0 && it == 2 && tl_n < 3990 && (threadIdx.x & 31) == 0) { \
+    long long* _p = a.dbg + (role) * 8192; _p[1 + 2 * tl_n] = 2000; _p[2 + 2 * tl_n] = tlc_acc[0]; ++tl_n; _p[1 + 2 * tl_n] = 3000; _p[2 + 2 * tl_n] = tlc_acc[1]; ++tl_n; _p[0] = tl_n; } \
+    tlc_acc[0] = tlc_acc[1] = 0; } while (0)
+#define TL(role, code) do { if (a.dbg && blockIdx.x == 0 && it == 2 && tl_n < 4000 && ((role) != 0 || (threadIdx.x & 31) == 0)) { \
+    long long* _p = a.dbg + (role) * 8192; _p[1 + 2 * tl_n] = (code); _p[2 + 2 * tl_n] = clock64(); ++tl_n; _p[0] = tl_n; } } while (0)
 #else
+#define TL_DECL do { } while (0)
+#define TLC(i) do { } while (0)
+#define TLC_FLUSH(role) do { } while (0)
 #define TL(role, code) do { } while (0)
 #endif
 
@@ -149,6 +158,16 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int
              threadIdx.x, parity);
       __trap();
     }
+  }
+}
+
+// Same bounded wait without the printf (a call inside the MMA warp's loop would force every loop-carried value
+// out of the uniform registers): the trap alone still turns a protocol bug into a failed launch.
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
 

@@ -16,7 +16,7 @@ lib = _cabi.lib()
 lib.s2l_debug_set_timeline.argtypes = [C.c_void_p]
 for _ in range(2):
     r.render_frames(audio, idx, 256, 256)
-buf = torch.zeros(3 * 2048, dtype=torch.int64, device=dev)
+buf = torch.zeros(3 * 8192, dtype=torch.int64, device=dev)
 lib.s2l_debug_set_timeline(C.c_void_p(buf.data_ptr()))
 r.render_frames(audio, idx, 256, 256)
 torch.cuda.synchronize()
@@ -24,10 +24,14 @@ lib.s2l_debug_set_timeline(None)
 b = buf.cpu().tolist()
 ev = []
 for role in range(3):
-    n = b[role * 2048]
+    n = b[role * 8192]
     for i in range(n):
-        ev.append((b[role * 2048 + 2 + 2 * i], role, b[role * 2048 + 1 + 2 * i]))
-ev.sort()
-t0 = ev[0][0]
+        ev.append((b[role * 8192 + 2 + 2 * i], role, b[role * 8192 + 1 + 2 * i]))
+stamps = [e for e in ev if e[2] not in (2000, 3000)]
+t0 = min(e[0] for e in stamps)
+# log order is kept per role (codes 2000 / 3000 carry durations, not timestamps: waits of the half just logged)
 for t, role, code in ev:
-    print("%8d  %s  %d" % (t - t0, ["MMA ", "EPI8", "EPI12"][role], code))
+    if code in (2000, 3000):
+        print("%8d  %s  %d  dur" % (t, ["MMA ", "EPI8", "EPI12"][role], code))
+    else:
+        print("%8d  %s  %d" % (t - t0, ["MMA ", "EPI8", "EPI12"][role], code))
