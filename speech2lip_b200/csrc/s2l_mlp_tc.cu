@@ -33,6 +33,7 @@
 // Warp roles (512 threads): w0 weight producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
 // w4-7 PE producers, w8-15 epilogue (two warps per TMEM lane quadrant, 32 columns each).
 #include <cstdlib>
+#include <type_traits>
 #include "s2l_tc_common.cuh"
 
 namespace s2l {
@@ -125,10 +126,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer
-    // The whole warp walks the layer program in lock step (so every address / descriptor below is computed on the
-    // uniform datapath, off the critical path); one elected lane issues the tcgen05 instructions of a granule
-    // back to back: one barrier wait and one commit per 8-12 MMAs.
-    uint32_t stage = 0, phase = 0;
+    // The whole warp walks the layer program in lock step, so every address / descriptor is computed on the uniform
+    // datapath; one elected lane issues the tcgen05 instructions.  The program is STATIC: ring stage, operand offsets
+    // and instruction descriptors of every MMA are compile-time constants relative to a few per-tile bases (the ring
+    // has 4 stages and every layer uses a multiple of... 2/8/10/8/4 granules, so the stage at each program point is
+    // fixed: G0 starts at 0, G1-4 at 2, G5 at 2, G6-7 at 0, G8 at 0), which brings the issue cost per MMA well under
+    // the 64 tensor-pipe cycles it covers — the issuing thread must run AHEAD of the pipe (queue depth ~7 MMAs).
+    uint32_t ph = 0;                            // bit s = parity to wait for on b_full[s]
     uint32_t epi_par = 0;                       // bit hk = parity to wait for on epi_done[hk]
     int rp = 0;
     long long it = 0;
@@ -138,101 +142,157 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     constexpr uint32_t kDescHi64 = 0x80004020u; // SBO=32 (512 B atoms) | version=1 | SWIZZLE_64B: 8-bit operands, 64 K per row
     auto mk64 = [](uint32_t lo) -> uint64_t { return ((uint64_t)kDescHi64 << 32) | lo; };
     const uint32_t stg0 = ((smem_u32(smem + SM_STG) >> 4) & 0x3FFFu) | 0x10000u;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int buf = (int)(it & 1);
-      const uint32_t pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
+    uint32_t pe_hi = 0, d_region = 0, a_region = 0;
+    int buf = 0;
+
+    // One granule (ring stage STAGE): wait for its bytes, issue its 4 / 8 / 12 MMAs, release the stage.
+    //   IS_PE: A operand = this tile's positional-encoding image in shared memory (SS form), else TMEM (TS form)
+    //   SMALL: output layer (N = 16, 2 KB planes).  done0/done1: extra barriers committed after the last MMA.
+    auto granule = [&](auto stage_c, auto is_pe_c, auto small_c, uint32_t d_addr, uint32_t a_t, uint32_t acc0,
+                       uint64_t* done0, uint64_t* done1) {
+      constexpr int STAGE = decltype(stage_c)::value;
+      constexpr bool IS_PE = decltype(is_pe_c)::value;
+      constexpr bool SMALL = decltype(small_c)::value;
+      constexpr int n_mma = SMALL ? kOutPad : kGranRows;
+      constexpr uint32_t idesc = (NPASS == 2) ? idesc_f16(n_mma) : idesc_bf16(n_mma);
+      constexpr uint32_t idesc_rw = idesc_f8(n_mma, 0u, 1u);     // (A - fp16 A) [e4m3] x fp16(W) [e5m2]
+      constexpr uint32_t idesc_wr = idesc_f8(n_mma, 1u, 0u);     // fp16(A) [e5m2] x (W - fp16 W) [e4m3]
+      constexpr uint32_t plane16 = (uint32_t)((SMALL ? kOutPlane : kGranPlane) >> 4);
+      TLC(1);
+      mbar_wait_trap(&b_full[STAGE], (ph >> STAGE) & 1u);
+      TLC(2);
+      ph ^= 1u << STAGE;
+      tc_fence_after();
+      const uint32_t b = stg0 + (uint32_t)STAGE * (uint32_t)(T1_STAGE >> 4);      // first plane: hi / fp16
+      const uint32_t b2 = b + plane16;                                            // second plane: lo / [e5m2 | e4m3]
+      const uint32_t b4 = b2 + (plane16 >> 1);
       const uint32_t pe_lo = pe_hi + (PE_PLANE >> 4);
       const uint32_t pe_e5 = pe_lo, pe_e4 = pe_lo + (PE_PLANE >> 5);      // NPASS == 2: [fp16 16 KB | e5m2 8 KB | e4m3 8 KB]
-#pragma unroll 1
-      for (int g = 0; g < kNumG; ++g) {
-        const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
-        const uint32_t a_region = tmem_base + (rp ? 0u : 256u);
-        const int nh = (g == 8) ? 1 : 2;
-        const int n_mma = (g == 8) ? kOutPad : kGranRows;
-        const uint32_t idesc = (NPASS == 2) ? idesc_f16(n_mma) : idesc_bf16(n_mma);
-        const uint32_t idesc_rw = idesc_f8(n_mma, 0u, 1u);     // (A - fp16 A) [e4m3] x fp16(W) [e5m2]
-        const uint32_t idesc_wr = idesc_f8(n_mma, 1u, 0u);     // fp16(A) [e5m2] x (W - fp16 W) [e4m3]
-        const uint32_t plane16 = (uint32_t)(((g == 8) ? kOutPlane : kGranPlane) >> 4);   // second plane of the granule
-        const int nkc = g_nkc(g);
-        if (g == 0) mbar_wait_trap(&pe_full[buf], (uint32_t)((it >> 1) & 1));
-#pragma unroll 1
-        for (int h = 0; h < nh; ++h) {
-          const uint32_t d_addr = d_region + (uint32_t)h * 128u;
-          TL(0, 1000 + g * 10 + h);                       // MMA warp starts half h of layer g
-#pragma unroll 1
-          for (int kc = 0; kc < nkc; ++kc) {
-            const bool is_pe = (g == 0) || (g == 5 && kc == 0);
-            const int hk = (g == 5) ? kc - 1 : kc;
-            TLC(0);
-            if (h == 0 && !is_pe) {
-              mbar_wait_trap(&epi_done[hk], (epi_par >> hk) & 1u);
-              epi_par ^= 1u << hk;
-            }
-            TLC(1);
-            mbar_wait_trap(&b_full[stage], phase);
-            TLC(2);
-            tc_fence_after();
-            // A chunk layout in TMEM (64 cols): bf16: [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
-            //                                   fp16f8, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
-            const uint32_t a_t = a_region + (uint32_t)hk * 64u;
-            const uint32_t b = stg0 + stage * (uint32_t)(T1_STAGE >> 4);      // first plane: hi / fp16
-            const uint32_t b2 = b + plane16;                                  // second plane: lo / [e5m2 | e4m3]
-            const uint32_t acc0 = (kc == 0) ? 0u : 1u;
-            if (elect_one()) {
-              if (is_pe) {
+      if (elect_one()) {
+        if (IS_PE) {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                  umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, s == 0 ? acc0 : 1u);
-                  if (NPASS == 3) umma_ss(d_addr, mk(pe_lo + 2 * s), mk(b + 2 * s), idesc, 1u);
-                }
-                if (NPASS == 3) {
-#pragma unroll
-                  for (int s = 0; s < 4; ++s) umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b2 + 2 * s), idesc, 1u);
-                }
-                if (NPASS == 2) {
-                  const uint32_t b4 = b2 + (plane16 >> 1);
-#pragma unroll
-                  for (int t = 0; t < 2; ++t) umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b2 + 2 * t), idesc_rw, 1u);
-#pragma unroll
-                  for (int t = 0; t < 2; ++t) umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
-                }
-              } else {
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                  const uint32_t a_hi = a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8);
-                  umma_ts(d_addr, a_hi, mk(b + 2 * s), idesc, s == 0 ? acc0 : 1u);
-                  if (NPASS == 3) umma_ts(d_addr, a_hi + 16u, mk(b + 2 * s), idesc, 1u);
-                }
-                if (NPASS == 3) {
-#pragma unroll
-                  for (int s = 0; s < 4; ++s)
-                    umma_ts(d_addr, a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8), mk(b2 + 2 * s), idesc, 1u);
-                }
-                if (NPASS == 2) {
-                  const uint32_t b4 = b2 + (plane16 >> 1);
-                  // same-format MMAs are issued back to back (operand formats live in the instruction descriptor)
-#pragma unroll
-                  for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b2 + 2 * t), idesc_rw, 1u);
-#pragma unroll
-                  for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
-                }
-              }
-              umma_commit(&b_empty[stage]);      // stage reusable once these MMAs retire
-              if (kc == nkc - 1) {
-                umma_commit(&acc_full[h]);       // accumulator half h of layer g complete
-                if (g == 5 && h == 1) umma_commit(&pe_empty[buf]);   // last reader of this tile's PE image
-              }
-            }
-            __syncwarp();
-            stage = (stage + 1) & (T1_NSTG - 1);
-            phase ^= (stage == 0);
+          for (int s = 0; s < 4; ++s) {
+            umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b + 2 * s), idesc, s == 0 ? acc0 : 1u);
+            if (NPASS == 3) umma_ss(d_addr, mk(pe_lo + 2 * s), mk(b + 2 * s), idesc, 1u);
           }
-          TL(0, 5000 + g * 10 + h);
-          TLC_FLUSH(0);
+          if (NPASS == 3) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) umma_ss(d_addr, mk(pe_hi + 2 * s), mk(b2 + 2 * s), idesc, 1u);
+          }
+          if (NPASS == 2) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) umma8_ss(d_addr, mk64(pe_e4 + 2 * t), mk64(b2 + 2 * t), idesc_rw, 1u);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) umma8_ss(d_addr, mk64(pe_e5 + 2 * t), mk64(b4 + 2 * t), idesc_wr, 1u);
+          }
+        } else {
+          // A chunk layout in TMEM (64 cols): bf16: [hi K0-31 (16) | lo K0-31 (16) | hi K32-63 (16) | lo K32-63 (16)]
+          //                                   fp16f8, per 32-K half: [fp16 (16 cols) | e5m2 (8) | e4m3 (8)]
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            const uint32_t a_hi = a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8);
+            umma_ts(d_addr, a_hi, mk(b + 2 * s), idesc, s == 0 ? acc0 : 1u);
+            if (NPASS == 3) umma_ts(d_addr, a_hi + 16u, mk(b + 2 * s), idesc, 1u);
+          }
+          if (NPASS == 3) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              umma_ts(d_addr, a_t + (uint32_t)((s >> 1) * 32 + (s & 1) * 8), mk(b2 + 2 * s), idesc, 1u);
+          }
+          if (NPASS == 2) {
+            // same-format MMAs are issued back to back (operand formats live in the instruction descriptor)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 24), mk64(b2 + 2 * t), idesc_rw, 1u);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
+          }
         }
-        rp ^= 1;
+        umma_commit(&b_empty[STAGE]);      // stage reusable once these MMAs retire
+        if (done0) umma_commit(done0);
+        if (done1) umma_commit(done1);
       }
+      __syncwarp();
+    };
+    auto wait_quarter = [&](int hk) {       // quarter hk of the previous layer's output converted to operand form
+      TLC(0);
+      mbar_wait_trap(&epi_done[hk], (epi_par >> hk) & 1u);
+      epi_par ^= 1u << hk;
+    };
+    using std::integral_constant;
+    auto I = [](auto v) { return v; };
+    (void)I;
+#define S2L_IC(v) integral_constant<int, (v)>{}
+#define S2L_BC(v) integral_constant<bool, (v)>{}
+    // hidden layer (4 K-chunks per accumulator half), ring position START at entry
+    auto layer_std = [&](auto start_c, int g) {
+      constexpr int START = decltype(start_c)::value;
+      (void)g;
+      TL(0, 1000 + g * 10);
+      wait_quarter(0); granule(S2L_IC((START + 0) & 3), S2L_BC(false), S2L_BC(false), d_region, a_region, 0u, nullptr, nullptr);
+      wait_quarter(1); granule(S2L_IC((START + 1) & 3), S2L_BC(false), S2L_BC(false), d_region, a_region + 64u, 1u, nullptr, nullptr);
+      wait_quarter(2); granule(S2L_IC((START + 2) & 3), S2L_BC(false), S2L_BC(false), d_region, a_region + 128u, 1u, nullptr, nullptr);
+      wait_quarter(3); granule(S2L_IC((START + 3) & 3), S2L_BC(false), S2L_BC(false), d_region, a_region + 192u, 1u, &acc_full[0], nullptr);
+      TL(0, 5000 + g * 10); TLC_FLUSH(0); TL(0, 1001 + g * 10);
+      granule(S2L_IC((START + 0) & 3), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region, 0u, nullptr, nullptr);
+      granule(S2L_IC((START + 1) & 3), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 64u, 1u, nullptr, nullptr);
+      granule(S2L_IC((START + 2) & 3), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 128u, 1u, nullptr, nullptr);
+      granule(S2L_IC((START + 3) & 3), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 192u, 1u, &acc_full[1], nullptr);
+      TL(0, 5001 + g * 10); TLC_FLUSH(0);
+    };
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      buf = (int)(it & 1);
+      pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
+      auto set_regions = [&]() {
+        d_region = tmem_base + (rp ? 256u : 0u);
+        a_region = tmem_base + (rp ? 0u : 256u);
+        rp ^= 1;
+      };
+      // ---- G0: PE x fold0 (stages 0, 1)
+      set_regions();
+      mbar_wait_trap(&pe_full[buf], (uint32_t)((it >> 1) & 1));
+      TL(0, 1000);
+      granule(S2L_IC(0), S2L_BC(true), S2L_BC(false), d_region, 0u, 0u, &acc_full[0], nullptr);
+      TL(0, 5000); TLC_FLUSH(0); TL(0, 1001);
+      granule(S2L_IC(1), S2L_BC(true), S2L_BC(false), d_region + 128u, 0u, 0u, &acc_full[1], nullptr);
+      TL(0, 5001); TLC_FLUSH(0);
+      // ---- G1-4 (ring position 2)
+#pragma unroll 1
+      for (int g = 1; g <= 4; ++g) {
+        set_regions();
+        layer_std(S2L_IC(2), g);
+      }
+      // ---- G5: PE x fold5 + W5b x h (5 granules per half; ring position 2, then 3)
+      set_regions();
+      TL(0, 1050);
+      granule(S2L_IC(2), S2L_BC(true), S2L_BC(false), d_region, 0u, 0u, nullptr, nullptr);
+      wait_quarter(0); granule(S2L_IC(3), S2L_BC(false), S2L_BC(false), d_region, a_region, 1u, nullptr, nullptr);
+      wait_quarter(1); granule(S2L_IC(0), S2L_BC(false), S2L_BC(false), d_region, a_region + 64u, 1u, nullptr, nullptr);
+      wait_quarter(2); granule(S2L_IC(1), S2L_BC(false), S2L_BC(false), d_region, a_region + 128u, 1u, nullptr, nullptr);
+      wait_quarter(3); granule(S2L_IC(2), S2L_BC(false), S2L_BC(false), d_region, a_region + 192u, 1u, &acc_full[0], nullptr);
+      TL(0, 5050); TLC_FLUSH(0); TL(0, 1051);
+      granule(S2L_IC(3), S2L_BC(true), S2L_BC(false), d_region + 128u, 0u, 0u, nullptr, nullptr);
+      granule(S2L_IC(0), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region, 1u, nullptr, nullptr);
+      granule(S2L_IC(1), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 64u, 1u, nullptr, nullptr);
+      granule(S2L_IC(2), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 128u, 1u, nullptr, nullptr);
+      granule(S2L_IC(3), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 192u, 1u, &acc_full[1], &pe_empty[buf]);   // last reader of this tile's PE image
+      TL(0, 5051); TLC_FLUSH(0);
+      // ---- G6-7 (ring position 0)
+#pragma unroll 1
+      for (int g = 6; g <= 7; ++g) {
+        set_regions();
+        layer_std(S2L_IC(0), g);
+      }
+      // ---- G8: output layer, N = 16 (ring position 0)
+      set_regions();
+      TL(0, 1080);
+      wait_quarter(0); granule(S2L_IC(0), S2L_BC(false), S2L_BC(true), d_region, a_region, 0u, nullptr, nullptr);
+      wait_quarter(1); granule(S2L_IC(1), S2L_BC(false), S2L_BC(true), d_region, a_region + 64u, 1u, nullptr, nullptr);
+      wait_quarter(2); granule(S2L_IC(2), S2L_BC(false), S2L_BC(true), d_region, a_region + 128u, 1u, nullptr, nullptr);
+      wait_quarter(3); granule(S2L_IC(3), S2L_BC(false), S2L_BC(true), d_region, a_region + 192u, 1u, &acc_full[0], nullptr);
+      TL(0, 5080); TLC_FLUSH(0);
     }
+#undef S2L_IC
+#undef S2L_BC
   } else if (warp >= 4 && warp < 8) {
     // =============================================================== PE producers (one point per thread)
     const int r = tid - 128;

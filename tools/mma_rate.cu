@@ -189,6 +189,50 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int variant, int n_iter, l
   }
 }
 
+// Queue-depth probe: issue n MMAs back to back (fp16 TS N=128), stamp the clock when the LAST ISSUE returns and when
+// the commit lands: the issue time stays ~flat per MMA until the tensor pipe's queue is full.
+__global__ void __launch_bounds__(128, 1) depth_kernel(int n, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM_MISC);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (SM_MISC) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x38343038u;
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  if (warp == 1 && elect_one()) {
+    const uint32_t b_s = ((smem_u32(smem + SM_B) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t idesc = idesc_f16(128);
+    const long long t0 = clock64();
+    if (n == 0) {   // best case: 12 MMAs fully unrolled with compile-time operand offsets
+#pragma unroll
+      for (int i = 0; i < 12; ++i) umma_ts(tmem_base, tmem_base + 256u + (uint32_t)((i & 7) * 8), dsc(0x40004040u, b_s + 2 * (i & 3) + 1024 * (i >> 2)), idesc, 1u);
+    } else {
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) umma_ts(tmem_base, tmem_base + 256u + (uint32_t)((i & 7) * 8), dsc(0x40004040u, b_s + 2 * (i & 3)), idesc, 1u);
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 int main(int argc, char** argv) {
   const int n_iter = argc > 1 ? atoi(argv[1]) : 512;
   const char* names[] = {"bf16 TS N128", "fp16 SS N128", "fp16 TS N256", "fp8 TS N128 e4m3xe5m2 SW64", "fp8 TS N128 fmt-alternating",
@@ -202,6 +246,15 @@ int main(int argc, char** argv) {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
   std::vector<long long> h(148);
+  if (argc > 3) {
+    cudaFuncSetAttribute(depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    for (int n : {0, 1, 2, 3, 4, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64}) {
+      for (int rep = 0; rep < 2; ++rep) { depth_kernel<<<1, 128, SMEM_BYTES>>>(n, d); cudaDeviceSynchronize(); }
+      cudaMemcpy(h.data(), d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+      printf("n %2d  issue-done %5lld cycles  complete %5lld cycles\n", n, h[0], h[1]);
+    }
+    return 0;
+  }
   for (int grid : {1, 148}) {
     for (int v = vfirst; v < nvar; ++v) {
       for (int rep = 0; rep < 2; ++rep) {
