@@ -68,6 +68,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   const long long n_tiles = a.tiles_per_frame * a.n_frames;
   const uint8_t* tcw = a.blob + (NPASS == 2 ? a.L.off_tcw8 : a.L.off_tcw);
 
+#ifdef S2L_TIMELINE
+  if (tid == 0 && blockIdx.x == 0 && a.dbg) {      // SM clock / wall clock pair at kernel start (effective frequency)
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.dbg[3 * 8192 + 0] = clock64();
+    a.dbg[3 * 8192 + 1] = (long long)gt;
+  }
+#endif
   if (tid == 0) {
     for (int s = 0; s < T1_NSTG; ++s) {
       mbar_init(&b_full[s], 1);
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       constexpr uint32_t idesc_rw = idesc_f8(n_mma, 0u, 1u);     // (A - fp16 A) [e4m3] x fp16(W) [e5m2]
       constexpr uint32_t idesc_wr = idesc_f8(n_mma, 1u, 0u);     // fp16(A) [e5m2] x (W - fp16 W) [e4m3]
       constexpr uint32_t plane16 = (uint32_t)((SMALL ? kOutPlane : kGranPlane) >> 4);
-      TLC(1);
+      TLC(3);
       mbar_wait_trap(&b_full[STAGE], (ph >> STAGE) & 1u);
       TLC(2);
       ph ^= 1u << STAGE;
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     auto wait_quarter = [&](int hk) {       // quarter hk of the previous layer's output converted to operand form
       TLC(0);
       mbar_wait_trap(&epi_done[hk], (epi_par >> hk) & 1u);
+      TLC(1);
       epi_par ^= 1u << hk;
     };
     using std::integral_constant;
@@ -422,41 +431,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             const uint32_t taddr = taddr0 + (uint32_t)(qq * 64);
             const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + half * 32);
             uint32_t o[32];
-            if (NPASS == 2) {
-              // [fp16 x 32 (16 cols) | e5m2(fp16(x) * 2^-kScaleW) x 32 (8 cols) | e4m3((x - fp16 x) * 2^kScaleA) x 32 (8 cols)]
-              constexpr float kDn = 1.0f / (float)(1 << kScaleW), kUp = (float)(1 << kScaleA);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 bb = b4[j4];
-                const uint32_t* v = qq ? vb : va;
-                const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
-                const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
-                const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
-                const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
-                const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                o[2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
-                o[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                o[16 + j4] = pack_fp8x4(f01.x * kDn, f01.y * kDn, f23.x * kDn, f23.y * kDn, __NV_E5M2);
-                o[24 + j4] = pack_fp8x4((x0 - f01.x) * kUp, (x1 - f01.y) * kUp, (x2 - f23.x) * kUp, (x3 - f23.y) * kUp, __NV_E4M3);
-              }
-            } else
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              const uint32_t* v = qq ? vb : va;
-              const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
-              const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
-              const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
-              const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
-              const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
-              o[2 * j4] = h0;
-              o[2 * j4 + 1] = h1;
-              if (NPASS == 3) {
-                o[16 + 2 * j4] = pack_bf16x2(x0 - __uint_as_float(h0 << 16), x1 - __uint_as_float(h0 & 0xffff0000u));
-                o[16 + 2 * j4 + 1] = pack_bf16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u));
-              }
-            }
+            if (qq) convert_slice<NPASS>(vb, b4, o);
+            else convert_slice<NPASS>(va, b4, o);
             if (NPASS != 1) tmem_st32(taddr, o);
             else tmem_st16(taddr, o);
             tmem_st_wait();
@@ -493,6 +469,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+#ifdef S2L_TIMELINE
+  if (tid == 0 && blockIdx.x == 0 && a.dbg) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.dbg[3 * 8192 + 2] = clock64();
+    a.dbg[3 * 8192 + 3] = (long long)gt;
+  }
+#endif
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");

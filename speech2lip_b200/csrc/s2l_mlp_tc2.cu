@@ -404,32 +404,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
             const uint32_t taddr = taddr0 + (uint32_t)(qq * 64);
             const float4* b4 = reinterpret_cast<const float4*>(bias + q * 64 + half * 32);
             uint32_t o[32];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bb = b4[j4];
-              const uint32_t* v = qq ? vb : va;
-              const float x0 = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bb.x, 0.f);
-              const float x1 = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bb.y, 0.f);
-              const float x2 = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bb.z, 0.f);
-              const float x3 = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bb.w, 0.f);
-              if (NPASS == 2) {
-                constexpr float kDn = 1.0f / (float)(1 << kScaleW), kUp = (float)(1 << kScaleA);
-                const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                o[2 * j4] = *reinterpret_cast<const uint32_t*>(&h01);
-                o[2 * j4 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-                o[16 + j4] = pack_fp8x4(f01.x * kDn, f01.y * kDn, f23.x * kDn, f23.y * kDn, __NV_E5M2);
-                o[24 + j4] = pack_fp8x4((x0 - f01.x) * kUp, (x1 - f01.y) * kUp, (x2 - f23.x) * kUp, (x3 - f23.y) * kUp, __NV_E4M3);
-              } else {
-                const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
-                o[2 * j4] = h0;
-                o[2 * j4 + 1] = h1;
-                if (NPASS == 3) {
-                  o[16 + 2 * j4] = pack_bf16x2(x0 - __uint_as_float(h0 << 16), x1 - __uint_as_float(h0 & 0xffff0000u));
-                  o[16 + 2 * j4 + 1] = pack_bf16x2(x2 - __uint_as_float(h1 << 16), x3 - __uint_as_float(h1 & 0xffff0000u));
-                }
-              }
-            }
+            if (qq) convert_slice<NPASS>(vb, b4, o);
+            else convert_slice<NPASS>(va, b4, o);
             if (NPASS != 1) tmem_st32(taddr, o);
             else tmem_st16(taddr, o);
             tmem_st_wait();

@@ -42,7 +42,7 @@ struct TcArgs {
 #ifdef S2L_TIMELINE
 #define TL_DECL int tl_n = 0; long long tlc_t[3] = {0, 0, 0}, tlc_acc[2] = {0, 0}
 // cheap wait accounting: TLC(i) stamps a register; TLC_FLUSH logs (epilogue-wait, weight-wait) cycles of the half as codes 2xxx/3xxx
-#define TLC(i) do { tlc_t[i] = clock64(); if ((i) == 1) tlc_acc[0] += tlc_t[1] - tlc_t[0]; if ((i) == 2) tlc_acc[1] += tlc_t[2] - tlc_t[1]; } while (0)
+#define TLC(i) do { if ((i) == 0) tlc_t[0] = clock64(); if ((i) == 1) tlc_acc[0] += clock64() - tlc_t[0]; if ((i) == 3) tlc_t[1] = clock64(); if ((i) == 2) tlc_acc[1] += clock64() - tlc_t[1]; } while (0)
 #define TLC_FLUSH(role) do { if (a.dbg && blockIdx.x == 0 && it == 2 && tl_n < 3990 && (threadIdx.x & 31) == 0) { \
     long long* _p = a.dbg + (role) * 8192; _p[1 + 2 * tl_n] = 2000; _p[2 + 2 * tl_n] = tlc_acc[0]; ++tl_n; _p[1 + 2 * tl_n] = 3000; _p[2 + 2 * tl_n] = tlc_acc[1]; ++tl_n; _p[0] = tl_n; } \
     tlc_acc[0] = tlc_acc[1] = 0; } while (0)
@@ -187,5 +187,87 @@ __device__ __forceinline__ uint32_t pack_fp8x4(float a, float b, float c, float 
   return lo | (hi << 16);
 }
 
+// ------------------------------------------------------------------ lean operand-split helpers (epilogue / PE)
+// Blackwell-only instructions keep the per-element conversion cost low: packed fp32 math (FADD2/FMUL2), the mixed
+// fp32/16-bit FMA (FHFMA: x - float(h) in ONE instruction, no unpack) and 2-wide narrowing converts (F2FP).
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// (x0 - float(h.lo), x1 - float(h.hi)) for a packed fp16 pair
+__device__ __forceinline__ float2 resid_f16x2(float x0, float x1, uint32_t h2) {
+  float2 r;
+  asm("{\n\t.reg .b16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %4;\n\tmov.b16 m1, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, lo, m1, %2;\n\tfma.rn.f32.f16 %1, hi, m1, %3;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(x0), "f"(x1), "r"(h2));
+  return r;
+}
+// same for a packed bf16 pair
+__device__ __forceinline__ float2 resid_bf16x2(float x0, float x1, uint32_t h2) {
+  float2 r;
+  asm("{\n\t.reg .b16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %4;\n\tmov.b16 m1, 0xBF80;\n\t"
+      "fma.rn.f32.bf16 %0, lo, m1, %2;\n\tfma.rn.f32.bf16 %1, hi, m1, %3;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(x0), "f"(x1), "r"(h2));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo, float hi) {        // element 0 in the low byte
+  uint16_t d;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_e5m2x2_f16x2(uint32_t h2) {
+  uint16_t d;
+  asm("cvt.rn.satfinite.e5m2x2.f16x2 %0, %1;" : "=h"(d) : "r"(h2));
+  return d;
+}
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// fp16f8 split of four non-negative-or-any fp32 values: fp16 pairs h01/h23, e5m2(fp16(x) * 2^-kScaleW) x4, e4m3((x - fp16 x) * 2^kScaleA) x4
+__device__ __forceinline__ void split4_fp16f8(float x0, float x1, float x2, float x3, uint32_t& h01, uint32_t& h23, uint32_t& w5, uint32_t& w4) {
+  constexpr uint32_t kDnH2 = (uint32_t)(((15 - kScaleW) << 10) | (((15 - kScaleW) << 10) << 16));   // fp16 2^-kScaleW, twice
+  constexpr float kUp = (float)(1 << kScaleA);
+  h01 = cvt_f16x2(x0, x1);
+  h23 = cvt_f16x2(x2, x3);
+  const float2 r01 = __fmul2_rn(resid_f16x2(x0, x1, h01), make_float2(kUp, kUp));
+  const float2 r23 = __fmul2_rn(resid_f16x2(x2, x3, h23), make_float2(kUp, kUp));
+  w4 = cvt_e4m3x2(r01.x, r01.y) | (cvt_e4m3x2(r23.x, r23.y) << 16);
+  w5 = cvt_e5m2x2_f16x2(hmul2_u32(h01, kDnH2)) | (cvt_e5m2x2_f16x2(hmul2_u32(h23, kDnH2)) << 16);
+}
+
+// One 32-column slice of an accumulator quarter -> next layer's A operand words (bias, ReLU, precision split), shared
+// by the single-CTA and CTA-pair kernels so both produce bit-identical operands.
+//   NPASS 3: o[0..15] bf16 hi pairs, o[16..31] bf16 lo pairs;   NPASS 1: o[0..15] bf16 pairs
+//   NPASS 2: o[0..15] fp16 pairs, o[16..23] e5m2(fp16(x) * 2^-kScaleW) x4, o[24..31] e4m3((x - fp16 x) * 2^kScaleA) x4
+template <int NPASS>
+__device__ __forceinline__ void convert_slice(const uint32_t (&v)[32], const float4* __restrict__ b4, uint32_t (&o)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 bb = b4[j4];
+    const float2 t01 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j4 + 0]), __uint_as_float(v[4 * j4 + 1])), make_float2(bb.x, bb.y));
+    const float2 t23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(bb.z, bb.w));
+    const float x0 = fmaxf(t01.x, 0.f), x1 = fmaxf(t01.y, 0.f), x2 = fmaxf(t23.x, 0.f), x3 = fmaxf(t23.y, 0.f);
+    if (NPASS == 2) {
+      split4_fp16f8(x0, x1, x2, x3, o[2 * j4], o[2 * j4 + 1], o[16 + j4], o[24 + j4]);
+    } else {
+      const uint32_t h0 = cvt_bf16x2(x0, x1), h1 = cvt_bf16x2(x2, x3);
+      o[2 * j4] = h0;
+      o[2 * j4 + 1] = h1;
+      if (NPASS == 3) {
+        const float2 r01 = resid_bf16x2(x0, x1, h0), r23 = resid_bf16x2(x2, x3, h1);
+        o[16 + 2 * j4] = cvt_bf16x2(r01.x, r01.y);
+        o[16 + 2 * j4 + 1] = cvt_bf16x2(r23.x, r23.y);
+      }
+    }
+  }
+}
 
 }  // namespace s2l

@@ -10,18 +10,22 @@ dev = torch.device("cuda:0")
 sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
 w = s2l.PackedWeights(sd)
 r = s2l.LipRenderer(w, prec)
-audio = torch.from_numpy(synth.make_audio(8, seed=1)).to(dev)
-idx = torch.arange(8)
+F = int(os.environ.get('S2L_TL_FRAMES', '64'))
+audio = torch.from_numpy(synth.make_audio(F, seed=1)).to(dev)
+idx = torch.arange(F)
 lib = _cabi.lib()
 lib.s2l_debug_set_timeline.argtypes = [C.c_void_p]
-for _ in range(2):
+for _ in range(6):
     r.render_frames(audio, idx, 256, 256)
-buf = torch.zeros(3 * 8192, dtype=torch.int64, device=dev)
+buf = torch.zeros(4 * 8192, dtype=torch.int64, device=dev)
 lib.s2l_debug_set_timeline(C.c_void_p(buf.data_ptr()))
 r.render_frames(audio, idx, 256, 256)
 torch.cuda.synchronize()
 lib.s2l_debug_set_timeline(None)
 b = buf.cpu().tolist()
+c0, g0, c1, g1 = b[3 * 8192: 3 * 8192 + 4]
+if g1 > g0:
+    print('# kernel: %d SM cycles in %.3f ms -> %.3f GHz effective SM clock' % (c1 - c0, (g1 - g0) / 1e6, (c1 - c0) / (g1 - g0)))
 ev = []
 for role in range(3):
     n = b[role * 8192]
