@@ -376,7 +376,7 @@ def run_gpu_arm(a):
                     "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor" if tensor_bound else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": None, "kernel": "mlp_tc_kernel" if tensor_bound else "mlp_fp32_kernel",
+                         "traffic": ncu_traffic(F, P), "kernel": "mlp_tc_kernel" if tensor_bound else "mlp_fp32_kernel",
                          "kernel_ms_per_launch": ker_ms / a.steps, "flop_per_point_algorithmic": FLOP_PER_POINT[a.mode],
                          "mma_multiplier": {"bf16x3": 3, "fp16f8": 2}.get(a.precision, 1), "peak_source": peak_src,
                          "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None,
@@ -404,6 +404,17 @@ def run_gpu_arm(a):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(frames, pts_per_frame):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel from the committed ncu capture
+    (profiles/ncu_traffic.json), scaled from the captured launch to this launch's point count; None if absent."""
+    try:
+        import json as _j
+        t = _j.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (float(frames) * pts_per_frame / t["points_per_launch"])
+    except Exception:
+        return None
 
 
 def main():
