@@ -360,6 +360,7 @@ def run_gpu_arm(a):
         else:
             peak, peak_src = 72.0, "nominal fp32 FFMA peak 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 figure)"
         flop_launch = float(F) * P * FLOP_PER_POINT[a.mode]
+        tc_sched = int(lib.s2l_tc_schedule((F * P + 127) // 128))      # 1 single CTAs, 2 CTA pairs, 3 multicast clusters
         ach = flop_launch / (ker_ms / a.steps * 1e-3) / 1e12
         frames_total = F * world * a.steps
         line = {
@@ -367,7 +368,7 @@ def run_gpu_arm(a):
             "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": {"bf16x3": "bf16x3-split (fp32 accumulate)", "bf16x1": "bf16", "fp32": "f32", "fp16f8": "fp16 + 2x fp8 corrections (fp32 accumulate)"}[a.precision], "data": "synthetic",
-            "config": {"workload": workload_name(a), "mode": a.mode, "precision": a.precision,
+            "config": {"workload": workload_name(a), "mode": a.mode, "precision": a.precision, "tc_schedule": tc_sched,
                        "points_per_frame": P, "weights": "synthetic kaiming-normal ('trained-like'), seed 0",
                        "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
                        "parallelism": "frames sharded across ranks, 1 NCCL weight broadcast at start, none during render"},
@@ -376,7 +377,7 @@ def run_gpu_arm(a):
                     "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor" if tensor_bound else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(F, P), "kernel": "mlp_tc_kernel" if tensor_bound else "mlp_fp32_kernel",
+                         "traffic": ncu_traffic(F, P), "kernel": ({1: "mlp_tc_kernel", 2: "mlp_tc2_kernel (CTA pairs)", 3: "mlp_tc_kernel (2-CTA multicast weights)"}[tc_sched] if tensor_bound else "mlp_fp32_kernel"),
                          "kernel_ms_per_launch": ker_ms / a.steps, "flop_per_point_algorithmic": FLOP_PER_POINT[a.mode],
                          "mma_multiplier": {"bf16x3": 3, "fp16f8": 2}.get(a.precision, 1), "peak_source": peak_src,
                          "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None,

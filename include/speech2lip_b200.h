@@ -192,6 +192,10 @@ int32_t s2l_frames_to_bgr8(const float* rgb, int64_t n_pixels, uint8_t* bgr, voi
 /* Number of kernels of this library launched by this thread since the last reset (bench "gpu_launches"). */
 int64_t s2l_launch_count(int32_t reset);
 
+/* Which tensor-core schedule a launch of n_tiles 128-point tiles uses: 1 independent CTAs, 2 CTA pairs (cta_group::2),
+ * 3 two-CTA clusters with one multicast weight stream.  S2L_TC_IMPL=1|2|3 forces one (see s2l_mlp_tc.cu). */
+int32_t s2l_tc_schedule(int64_t n_tiles);
+
 #ifdef __cplusplus
 }
 #endif

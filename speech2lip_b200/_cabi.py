@@ -61,6 +61,7 @@ SYMBOLS = {
     "s2l_audio_windows": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "s2l_frames_to_bgr8": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "s2l_launch_count": (C.c_int64, [C.c_int32]),
+    "s2l_tc_schedule": (C.c_int32, [C.c_int64]),
 }
 
 _lib = None

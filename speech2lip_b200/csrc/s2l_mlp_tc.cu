@@ -49,7 +49,11 @@ constexpr int T1_SM_TMEMPTR = T1_SM_BAR + T1_NBAR * 8;
 constexpr int T1_SMEM_BYTES = T1_SM_TMEMPTR + 16;
 static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
 
-template <int NPASS, int UVD>
+// CL = 1: independent CTAs.  CL = 2: CTAs are launched as clusters of two that share ONE weight stream — each CTA
+// fetches half of every granule and multicasts it into both CTAs' rings, halving the L2 reads / crossbar traffic per
+// weight byte delivered (the stream costs ~270 W at full rate); MMAs, TMEM and epilogues stay per CTA,
+// the only coupling is the ring (a stage is refilled when BOTH CTAs released it).
+template <int NPASS, int UVD, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T1_SM_BAR);
@@ -66,6 +70,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches and the MMA warp's loop state stay on the uniform datapath
   const long long n_tiles = a.tiles_per_frame * a.n_frames;
+  // every CTA runs the same number of tile iterations (a cluster shares the weight ring, so it must stay in lock step);
+  // iterations past the end work on zero rows and store nothing
+  const long long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long tile_end = (long long)blockIdx.x + n_iter * gridDim.x;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
   const uint8_t* tcw = a.blob + (NPASS == 2 ? a.L.off_tcw8 : a.L.off_tcw);
 
 #ifdef S2L_TIMELINE
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   if (tid == 0) {
     for (int s = 0; s < T1_NSTG; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], CL);       // released by the MMA warp of every CTA sharing the stream
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&pe_full[b], 128);
@@ -102,6 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peer barriers initialised before any multicast copy / commit can land
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_s, 0);
 
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // One stage = one granule (both planes of a [128 N x 64 K] weight tile, contiguous in the blob) = ONE bulk copy.
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
 #pragma unroll 1
         for (int g = 0; g < kNumG; ++g) {
           const int ngran = (g == 8) ? 4 : 2 * g_nkc(g);
@@ -119,12 +130,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const uint8_t* src = tcw + g_layer_off(g);
 #pragma unroll 1
           for (int gi = 0; gi < ngran; ++gi) {
+#ifdef S2L_DBG_PRODSPIN
+            mbar_wait_wd<false>(&b_empty[stage], phase ^ 1u, 100 + stage);
+#else
             mbar_wait_wd<true>(&b_empty[stage], phase ^ 1u, 100 + stage);
+#endif
 #ifdef S2L_DBG_NOLOAD        // experiment: weights are never streamed (results are garbage, timing only)
             mbar_arrive(&b_full[stage]);
 #else
+#ifdef S2L_DBG_HALFLOAD      // experiment: only half of every granule is streamed (what a CTA pair would fetch per SM)
+            mbar_arrive_expect_tx(&b_full[stage], bytes / 2);
+            bulk_g2s(smem + SM_STG + stage * T1_STAGE, src + (size_t)gi * gran, bytes / 2, &b_full[stage]);
+#else
             mbar_arrive_expect_tx(&b_full[stage], bytes);
-            bulk_g2s(smem + SM_STG + stage * T1_STAGE, src + (size_t)gi * gran, bytes, &b_full[stage]);
+            if (CL == 1) {
+              bulk_g2s(smem + SM_STG + stage * T1_STAGE, src + (size_t)gi * gran, bytes, &b_full[stage]);
+            } else {        // my slice of the granule, into every CTA of the cluster
+              const uint32_t slice = bytes / CL;
+              bulk_g2s_mc(smem + SM_STG + stage * T1_STAGE + crank * slice, src + (size_t)gi * gran + crank * slice, slice,
+                          &b_full[stage], kClMask);
+            }
+#endif
 #endif
             stage = (stage + 1) & (T1_NSTG - 1);
             phase ^= (stage == 0);
@@ -215,7 +241,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             for (int t = 0; t < 2; ++t) umma8_ts(d_addr, a_t + (uint32_t)(t * 32 + 16), mk64(b4 + 2 * t), idesc_wr, 1u);
           }
         }
-        umma_commit(&b_empty[STAGE]);      // stage reusable once these MMAs retire
+        if (CL == 1) umma_commit(&b_empty[STAGE]);      // stage reusable once these MMAs retire
+        else umma_commit_mc(&b_empty[STAGE], kClMask);  // ... in every CTA that multicasts into it
         if (done0) umma_commit(done0);
         if (done1) umma_commit(done1);
       }
@@ -248,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       granule(S2L_IC((START + 3) & 3), S2L_BC(false), S2L_BC(false), d_region + 128u, a_region + 192u, 1u, &acc_full[1], nullptr);
       TL(0, 5001 + g * 10); TLC_FLUSH(0);
     };
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       buf = (int)(it & 1);
       pe_hi = ((smem_u32(smem + SM_PE + buf * PE_BUF) >> 4) & 0x3FFFu) | 0x10000u;
       auto set_regions = [&]() {
@@ -306,83 +333,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // =============================================================== PE producers (one point per thread)
     const int r = tid - 128;
     long long it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      const int f = (int)(tile / a.tiles_per_frame);
-      const long long p = (tile % a.tiles_per_frame) * TC_TM + r;
+      const bool live = tile < n_tiles;
+      const int f = live ? (int)(tile / a.tiles_per_frame) : 0;
+      const long long p = live ? (tile % a.tiles_per_frame) * TC_TM + r : a.src.P;
       mbar_wait_wd<true>(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
-      float e[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) e[i] = 0.f;
-      if (p < a.src.P) {
-        float x[3];
-        gen_point(a.src, f, p, x);
-#pragma unroll
-        for (int d = 0; d < UVD; ++d) e[d] = x[d];
-#pragma unroll
-        for (int k = 0; k < kMultires; ++k) {
-#pragma unroll
-          for (int d = 0; d < UVD; ++d) {
-            float sn, cs;
-            sincosf(__fmul_rn(x[d], (float)(1 << k)), &sn, &cs);     // tf_nerf.py:412: p_fn(x * freq)
-            e[UVD + (2 * k) * UVD + d] = sn;
-            e[UVD + (2 * k + 1) * UVD + d] = cs;
-          }
-        }
-      }
-      uint8_t* hi_base = smem + SM_PE + buf * PE_BUF;
-      uint8_t* lo_base = hi_base + PE_PLANE;
-      const int row_off = (r >> 3) * 1024 + (r & 7) * 128;
-      if (NPASS == 2) {
-        // fp16 main image (SW128) + e5m2(fp16(e) * 2^-kScaleW) and e4m3((e - fp16 e) * 2^kScaleA) images (SW64)
-        constexpr float kDn = 1.0f / (float)(1 << kScaleW), kUp = (float)(1 << kScaleA);
-        uint8_t* e5_base = lo_base;
-        uint8_t* e4_base = lo_base + PE_PLANE / 2;
-        const int row_off64 = (r >> 3) * 512 + (r & 7) * 64;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {                 // 16 K-elements per 16-byte fp8 chunk
-          uint32_t w5[4], w4[4];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {               // two 8-element fp16 chunks
-            uint32_t h[4];
-            float f[8], rs[8];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float v0 = e[16 * c + 8 * u + 2 * t], v1 = e[16 * c + 8 * u + 2 * t + 1];
-              const __half2 hh = __floats2half2_rn(v0, v1);
-              h[t] = *reinterpret_cast<const uint32_t*>(&hh);
-              const float2 back = __half22float2(hh);
-              f[2 * t] = back.x; f[2 * t + 1] = back.y;
-              rs[2 * t] = v0 - back.x; rs[2 * t + 1] = v1 - back.y;
-            }
-            const int j = 2 * c + u;
-            *reinterpret_cast<uint4*>(hi_base + row_off + ((j ^ (r & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              w5[2 * u + t] = pack_fp8x4(f[4 * t] * kDn, f[4 * t + 1] * kDn, f[4 * t + 2] * kDn, f[4 * t + 3] * kDn, __NV_E5M2);
-              w4[2 * u + t] = pack_fp8x4(rs[4 * t] * kUp, rs[4 * t + 1] * kUp, rs[4 * t + 2] * kUp, rs[4 * t + 3] * kUp, __NV_E4M3);
-            }
-          }
-          const int off64 = row_off64 + ((c ^ ((r >> 1) & 3)) << 4);
-          *reinterpret_cast<uint4*>(e5_base + off64) = make_uint4(w5[0], w5[1], w5[2], w5[3]);
-          *reinterpret_cast<uint4*>(e4_base + off64) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        }
-      } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float v0 = e[8 * j + 2 * t], v1 = e[8 * j + 2 * t + 1];
-          const uint32_t hp = pack_bf16x2(v0, v1);
-          h[t] = hp;
-          l[t] = pack_bf16x2(v0 - __uint_as_float(hp << 16), v1 - __uint_as_float(hp & 0xffff0000u));
-        }
-        const int off = row_off + ((j ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        if (NPASS == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-      }
+      pe_write_row<NPASS, UVD>(a.src, f, p, p < a.src.P, r, smem + SM_PE + buf * PE_BUF);
       {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
         float* dst = fbias_s + buf * 512;
@@ -400,10 +357,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     int rp = 0;
     long long it = 0;
     TL_DECL;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      const int f = (int)(tile / a.tiles_per_frame);
-      const long long p = (tile % a.tiles_per_frame) * TC_TM + row;
+      const bool live = tile < n_tiles;
+      const int f = live ? (int)(tile / a.tiles_per_frame) : 0;
+      const long long p = live ? (tile % a.tiles_per_frame) * TC_TM + row : a.src.P;
       mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 600 + buf);   // folded per-frame biases staged
       for (int g = 0; g < 8; ++g) {
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
@@ -477,45 +435,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     a.dbg[3 * 8192 + 3] = (long long)gt;
   }
 #endif
+  if (CL > 1) cluster_sync_all();      // no CTA may retire while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
-template <int NPASS, int UVD>
+template <int NPASS, int UVD, int CL>
 static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
-    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM_BYTES) != cudaSuccess) {
       set_error("mlp_tc: cannot opt in to %d B of shared memory: %s", T1_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
       return 6;
     }
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  mlp_tc_kernel<NPASS, UVD><<<grid, TC_THREADS, T1_SMEM_BYTES, st>>>(a);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
+  const long long want = (n_tiles + CL - 1) / CL;
+  const unsigned grid = (unsigned)((want < sms / CL ? want : sms / CL) * CL);      // whole clusters, one CTA per SM
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = T1_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = CL;
+  at.val.clusterDim.y = 1;
+  at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, mlp_tc_kernel<NPASS, UVD, CL>, a);
   return check_launch("mlp_tc_kernel") ? 0 : 5;
+}
+
+template <int CL>
+static int launch_tc_cl(const TcArgs& a, long long n_tiles, int npass, int uvd, cudaStream_t st) {
+  if (uvd == 2)
+    return npass == 3 ? launch_tc_impl<3, 2, CL>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 2, CL>(a, n_tiles, st) : launch_tc_impl<1, 2, CL>(a, n_tiles, st);
+  return npass == 3 ? launch_tc_impl<3, 3, CL>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 3, CL>(a, n_tiles, st) : launch_tc_impl<1, 3, CL>(a, n_tiles, st);
 }
 
 int launch_mlp_tc2(const TcArgs& a, long long n_tiles, int npass, cudaStream_t st);   // s2l_mlp_tc2.cu (CTA pairs)
 
-// S2L_TC_IMPL=2 selects the CTA-pair (cta_group::2) kernel; the single-CTA kernel of this file is the default
-// (measured round 1, 4.19 M points: bf16x3 8.4 vs 8.4 ms, fp16f8 7.4 vs 8.4 ms, bf16x1 4.4 vs 5.6 ms).
-static int tc_impl() {
-  static int impl = 0;
-  if (impl == 0) {
+// Which tensor-core schedule runs a launch of n_tiles 128-point tiles:
+//   1 = independent CTAs (this file, CL = 1)          2 = CTA pairs, cta_group::2 MMAs sharing every B tile (s2l_mlp_tc2.cu)
+//   3 = independent MMAs, 2-CTA clusters sharing one multicast weight stream (this file, CL = 2)
+// S2L_TC_IMPL=1|2|3 forces one; by default launches that keep the whole chip busy for several tiles per SM use the pair
+// kernel (in the sustained, power-capped regime it halves the L2 -> SMEM weight bytes per SM: +6 % SM clock, +2.5-3 %
+// frames/s, round-1e measurements) and small launches the single-CTA kernel (shorter dependency chains: ~4 % faster in
+// short bursts).
+int tc_impl_for(long long n_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
     const char* e = getenv("S2L_TC_IMPL");
-    impl = (e && e[0] == '2') ? 2 : 1;
+    forced = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
   }
-  return impl;
+  if (forced) return forced;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (n_tiles >= 8ll * sms && sms % 2 == 0) ? 2 : 1;
 }
+extern "C" int32_t s2l_tc_schedule(int64_t n_tiles) { return tc_impl_for(n_tiles); }
 
 static long long* g_timeline = nullptr;
 extern "C" void s2l_debug_set_timeline(long long* buf) { g_timeline = buf; }     // debug builds (tools/tc_timeline.py)
@@ -535,13 +523,10 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   const long long n_tiles = a.tiles_per_frame * n_frames;
   if (n_tiles == 0) return 0;
   if (src.uv_dims != 2 && src.uv_dims != 3) { set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims); return 2; }
-  if (tc_impl() == 2) return launch_mlp_tc2(a, n_tiles, npass, st);
-  if (src.uv_dims == 2)
-    return npass == 3 ? launch_tc_impl<3, 2>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 2>(a, n_tiles, st) : launch_tc_impl<1, 2>(a, n_tiles, st);
-  if (src.uv_dims == 3)
-    return npass == 3 ? launch_tc_impl<3, 3>(a, n_tiles, st) : npass == 2 ? launch_tc_impl<2, 3>(a, n_tiles, st) : launch_tc_impl<1, 3>(a, n_tiles, st);
-  set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims);
-  return 2;
+  const int impl = tc_impl_for(n_tiles);
+  if (impl == 2) return launch_mlp_tc2(a, n_tiles, npass, st);
+  if (impl == 3) return launch_tc_cl<2>(a, n_tiles, npass, src.uv_dims, st);
+  return launch_tc_cl<1>(a, n_tiles, npass, src.uv_dims, st);
 }
 
 }  // namespace s2l

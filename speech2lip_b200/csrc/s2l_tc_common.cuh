@@ -146,9 +146,51 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// ------------------------------------------------------------------ thread-block-cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// relaxed flavour for events whose payload is NOT generic memory (TMEM stores already completed by tcgen05.wait::st,
+// async-proxy shared-memory writes already fenced): no cluster-scope release of the thread's earlier global stores
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in ctaMask, completion bytes credited to the
+// mbarrier at the same offset in each destination CTA
+__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// commit whose arrival is delivered to the barrier at this offset in every CTA of ctaMask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // Bounded mbarrier wait: a protocol bug must surface as a trapped kernel, never as a hung GPU box.
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef S2L_DBG_SUSPEND       // experiment: let the hardware park the warp (up to ~20 us) instead of polling
+  if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+#endif
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -267,6 +309,84 @@ __device__ __forceinline__ void convert_slice(const uint32_t (&v)[32], const flo
         o[16 + 2 * j4 + 1] = cvt_bf16x2(r23.x, r23.y);
       }
     }
+  }
+}
+
+// Positional encoding of one point (Embedder.__call__, tf_nerf.py:404-425: [x, sin(2^k x), cos(2^k x)]_k, zero-padded
+// to 64) written as row r of the K-major A-operand image(s) of a 128-row tile: bf16 hi (+ lo) SW128 planes, or for
+// NPASS == 2 the fp16 SW128 plane + e5m2 / e4m3 SW64 planes.  `valid` = the point exists (rows past the end are zeros).
+template <int NPASS, int UVD>
+__device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long long p, bool valid, int r, uint8_t* hi_base) {
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  if (valid) {
+    float x[3];
+    gen_point(src, f, p, x);
+#pragma unroll
+    for (int d = 0; d < UVD; ++d) e[d] = x[d];
+#pragma unroll
+    for (int k = 0; k < kMultires; ++k) {
+#pragma unroll
+      for (int d = 0; d < UVD; ++d) {
+        float sn, cs;
+        sincosf(__fmul_rn(x[d], (float)(1 << k)), &sn, &cs);     // tf_nerf.py:412: p_fn(x * freq)
+        e[UVD + (2 * k) * UVD + d] = sn;
+        e[UVD + (2 * k + 1) * UVD + d] = cs;
+      }
+    }
+  }
+  uint8_t* lo_base = hi_base + PE_PLANE;
+  const int row_off = (r >> 3) * 1024 + (r & 7) * 128;
+  if (NPASS == 2) {
+    // fp16 main image (SW128) + e5m2(fp16(e) * 2^-kScaleW) and e4m3((e - fp16 e) * 2^kScaleA) images (SW64)
+    constexpr float kDn = 1.0f / (float)(1 << kScaleW), kUp = (float)(1 << kScaleA);
+    uint8_t* e5_base = lo_base;
+    uint8_t* e4_base = lo_base + PE_PLANE / 2;
+    const int row_off64 = (r >> 3) * 512 + (r & 7) * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                 // 16 K-elements per 16-byte fp8 chunk
+      uint32_t w5[4], w4[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {               // two 8-element fp16 chunks
+        uint32_t h[4];
+        float f[8], rs[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float v0 = e[16 * c + 8 * u + 2 * t], v1 = e[16 * c + 8 * u + 2 * t + 1];
+          const __half2 hh = __floats2half2_rn(v0, v1);
+          h[t] = *reinterpret_cast<const uint32_t*>(&hh);
+          const float2 back = __half22float2(hh);
+          f[2 * t] = back.x; f[2 * t + 1] = back.y;
+          rs[2 * t] = v0 - back.x; rs[2 * t + 1] = v1 - back.y;
+        }
+        const int j = 2 * c + u;
+        *reinterpret_cast<uint4*>(hi_base + row_off + ((j ^ (r & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          w5[2 * u + t] = pack_fp8x4(f[4 * t] * kDn, f[4 * t + 1] * kDn, f[4 * t + 2] * kDn, f[4 * t + 3] * kDn, __NV_E5M2);
+          w4[2 * u + t] = pack_fp8x4(rs[4 * t] * kUp, rs[4 * t + 1] * kUp, rs[4 * t + 2] * kUp, rs[4 * t + 3] * kUp, __NV_E4M3);
+        }
+      }
+      const int off64 = row_off64 + ((c ^ ((r >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(e5_base + off64) = make_uint4(w5[0], w5[1], w5[2], w5[3]);
+      *reinterpret_cast<uint4*>(e4_base + off64) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  } else {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float v0 = e[8 * j + 2 * t], v1 = e[8 * j + 2 * t + 1];
+      const uint32_t hp = pack_bf16x2(v0, v1);
+      h[t] = hp;
+      l[t] = pack_bf16x2(v0 - __uint_as_float(hp << 16), v1 - __uint_as_float(hp & 0xffff0000u));
+    }
+    const int off = row_off + ((j ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (NPASS == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
   }
 }
 

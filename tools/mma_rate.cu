@@ -233,6 +233,104 @@ __global__ void __launch_bounds__(128, 1) depth_kernel(int n, long long* out) {
   }
 }
 
+// ---------------------------------------------------------------- cta_group::2 (CTA pair) issue rate
+__device__ __forceinline__ void umma2_ts_f16(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+               "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma2_ss_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma2_ts_f8(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+               "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_pair(uint32_t a_fmt, uint32_t b_fmt, int n) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pair_kernel(int variant, int n_iter, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM_MISC);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + SM_MISC + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = tid; i < (SM_MISC) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x38343038u + (uint32_t)(i & 3);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  {
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0x38343038u + (uint32_t)i;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    for (int c = 0; c < 256; c += 32) tmem_st32(tmem_base + lane_sel + 256u + (uint32_t)c, v);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  if (rank == 0 && warp == 1 && elect_one()) {
+    constexpr uint32_t kHi128 = 0x40004040u, kHi64 = 0x80004020u;
+    const uint32_t a_s = ((smem_u32(smem + SM_A) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t b_s = ((smem_u32(smem + SM_B) >> 4) & 0x3FFFu) | 0x10000u;
+    const uint32_t d0 = tmem_base, a_t = tmem_base + 256u;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+      const uint32_t bo = (uint32_t)(it & 3) * 1024u;
+      switch (variant) {
+        case 0:   // fp16 TS M=256 N=128 (64 B rows per CTA)
+#pragma unroll
+          for (int s = 0; s < 8; ++s) umma2_ts_f16(d0, a_t + (uint32_t)(s * 8), dsc(kHi128, b_s + bo + 2 * (s & 3)), idesc_pair(0, 0, 128), 1u);
+          break;
+        case 1:   // fp16 TS M=256 N=256
+#pragma unroll
+          for (int s = 0; s < 8; ++s) umma2_ts_f16(d0, a_t + (uint32_t)(s * 8), dsc(kHi128, b_s + bo + 2 * (s & 3)), idesc_pair(0, 0, 256), 1u);
+          break;
+        case 2:   // fp8 TS M=256 N=128
+#pragma unroll
+          for (int s = 0; s < 8; ++s) umma2_ts_f8(d0, a_t + (uint32_t)(s * 8), dsc(kHi64, b_s + bo + 2 * (s & 1)), idesc_pair(0, 1, 128), 1u);
+          break;
+        case 3:   // fp16 SS M=256 N=128
+#pragma unroll
+          for (int s = 0; s < 8; ++s) umma2_ss_f16(d0, dsc(kHi128, a_s + 2 * (s & 3)), dsc(kHi128, b_s + bo + 2 * (s & 3)), idesc_pair(0, 0, 128), 1u);
+          break;
+        case 4:   // fp16 TS M=256 N=64
+#pragma unroll
+          for (int s = 0; s < 8; ++s) umma2_ts_f16(d0, a_t + (uint32_t)(s * 8), dsc(kHi128, b_s + bo + 2 * (s & 3)), idesc_pair(0, 0, 64), 1u);
+          break;
+        case 5:   // fp16 TS M=256 N=128 alternating accumulator halves
+#pragma unroll
+          for (int s = 0; s < 8; ++s) umma2_ts_f16(d0 + (uint32_t)((s & 1) * 128), a_t + (uint32_t)(s * 8), dsc(kHi128, b_s + bo + 2 * (s & 3)), idesc_pair(0, 0, 128), 1u);
+          break;
+        default: break;
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)1) : "memory");
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x / 2] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 int main(int argc, char** argv) {
   const int n_iter = argc > 1 ? atoi(argv[1]) : 512;
   const char* names[] = {"bf16 TS N128", "fp16 SS N128", "fp16 TS N256", "fp8 TS N128 e4m3xe5m2 SW64", "fp8 TS N128 fmt-alternating",
@@ -246,6 +344,24 @@ int main(int argc, char** argv) {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
   std::vector<long long> h(148);
+  if (argc > 3 && argv[3][0] == 'p') {
+    const char* pn[] = {"pair fp16 TS M256 N128", "pair fp16 TS M256 N256", "pair fp8 TS M256 N128", "pair fp16 SS M256 N128", "pair fp16 TS M256 N64", "pair fp16 TS N128 alt D halves"};
+    cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    for (int grid : {2, 148}) {
+      for (int v = 0; v < 6; ++v) {
+        for (int rep = 0; rep < 2; ++rep) {
+          pair_kernel<<<grid, 128, SMEM_BYTES>>>(v, n_iter, d);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("pair variant %d: %s\n", v, cudaGetErrorString(e)); return 1; }
+        }
+        cudaMemcpy(h.data(), d, (grid / 2) * sizeof(long long), cudaMemcpyDeviceToHost);
+        std::sort(h.begin(), h.begin() + grid / 2);
+        const double per = 1.0 / (8.0 * n_iter);
+        printf("grid %3d  p%-2d %-34s cycles/MMA min %.1f med %.1f max %.1f\n", grid, v, pn[v], h[0] * per, h[grid / 4] * per, h[grid / 2 - 1] * per);
+      }
+    }
+    return 0;
+  }
   if (argc > 3) {
     cudaFuncSetAttribute(depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     for (int n : {0, 1, 2, 3, 4, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64}) {
