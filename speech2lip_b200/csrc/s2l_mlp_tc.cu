@@ -16,10 +16,13 @@
 //                 D_g -> A_{g+1} IN PLACE, one 64-column quarter at a time (tcgen05.ld -> +bias, ReLU,
 //                 bf16 hi/lo split -> tcgen05.st over the same columns), so the next layer's MMAs over
 //                 K-chunk q start as soon as quarter q is converted while later quarters still compute.
-//   weights     : streamed from L2 (blob TCW section, pre-swizzled smem images) by 1-D bulk copies
-//                 into a 9-stage ring of 16 KB planes (128 N-rows x 64 K, bf16; a granule = hi plane
-//                 then lo plane).  MMAs are M=128 x N=128 (one accumulator half) so that the single
-//                 issuing thread needs one instruction per 64 tensor-pipe cycles.
+//   weights     : streamed from L2 (blob TCW / TCW8 section, pre-swizzled smem images) into a 4-stage ring of
+//                 32 KB granules (both planes of a [128 N-rows x 64 K] weight tile, contiguous in the blob ->
+//                 ONE 1-D bulk copy, one barrier wait and one commit per 8-12 MMAs).  MMAs are M=128 x N=128
+//                 (one accumulator half, 64 tensor-pipe cycles) so the epilogue of half 0 overlaps the MMAs of
+//                 half 1.  The issuing warp runs converged on the uniform datapath with a STATIC program
+//                 (see the MMA-issuer role below): the pipe's queue is only ~7 MMAs deep, so the issuer has to
+//                 stay ahead of it.
 //   PE          : computed by 4 dedicated warps one tile ahead, written as a K-major SW128 bf16 hi/lo
 //                 A-operand image in shared memory (used by G0 and again by G5).
 //
@@ -30,7 +33,8 @@
 // bf16 rate) with power-of-two pre-scaling (e4m3 for the residuals, e5m2 for the full-range factors):
 // 1 + 0.5 + 0.5 = 2 bf16-MMA equivalents per product instead of 3, ~2^-15 relative per product.
 //
-// Warp roles (512 threads): w0 weight producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
+// Warp roles (512 threads): w0 weight producer (one lane), w1 MMA issuer (whole warp, one elected lane issues),
+// w2 TMEM allocator, w3 idle,
 // w4-7 PE producers, w8-15 epilogue (two warps per TMEM lane quadrant, 32 columns each).
 #include <cstdlib>
 #include <type_traits>
