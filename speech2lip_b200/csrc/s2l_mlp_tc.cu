@@ -55,7 +55,7 @@ static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
 
 // CL = 1: independent CTAs.  CL = 2: CTAs are launched as clusters of two that share ONE weight stream — each CTA
 // fetches half of every granule and multicasts it into both CTAs' rings, halving the L2 reads / crossbar traffic per
-// weight byte delivered (the stream costs ~270 W at full rate); MMAs, TMEM and epilogues stay per CTA,
+// weight byte delivered (worth ~+3 % sustained); MMAs, TMEM and epilogues stay per CTA,
 // the only coupling is the ring (a stage is refilled when BOTH CTAs released it).
 template <int NPASS, int UVD, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
