@@ -320,6 +320,9 @@ __device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long lo
   float e[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) e[i] = 0.f;
+#ifdef S2L_DBG_NOPE           // experiment: what the 60 sincosf per point cost (results are garbage, timing only)
+  valid = false;
+#endif
   if (valid) {
     float x[3];
     gen_point(src, f, p, x);

@@ -479,7 +479,11 @@ w = s2l.PackedWeights(sd)
 a = torch.from_numpy(synth.make_audio(3, seed=5)).to(dev)
 for prec in ("bf16x3", "fp16f8", "bf16x1"):
     out = s2l.LipRenderer(w, prec).render_frames(a, torch.tensor([1, 2, 3]), 37, 53)
-    torch.save(out.cpu(), sys.argv[1] + prec + ".pt")
+    # 2 x 76 = 152 tiles on 148 SMs: most CTAs run one live and one dead (past-the-end) tile iteration
+    out2 = s2l.LipRenderer(w, prec).render_frames(a[:2], torch.tensor([4, 5]), 100, 97)
+    torch.save([out.cpu(), out2.cpu()], sys.argv[1] + prec + ".pt")
+exact = s2l.LipRenderer(w, "fp32").render_frames(a[:2], torch.tensor([4, 5]), 100, 97)
+torch.save(exact.cpu(), sys.argv[1] + "fp32.pt")
 """ % ROOT
     import tempfile
     outs = {}
@@ -488,14 +492,22 @@ for prec in ("bf16x3", "fp16f8", "bf16x1"):
         env = dict(os.environ, S2L_TC_IMPL=impl)
         subprocess.run([sys.executable, "-c", code, d + "/"], check=True, env=env, timeout=600)
         outs[impl] = {p: torch.load(d + "/" + p + ".pt") for p in ("bf16x3", "fp16f8", "bf16x1")}
+        exact = torch.load(d + "/fp32.pt")
     for other in ("2", "3"):
         for p in ("bf16x3", "fp16f8", "bf16x1"):
-            err = (outs["1"][p] - outs[other][p]).abs().max().item()
-            print("impl 1 vs %s %s maxabs %.3e" % (other, p, err))
-            assert err < 2e-5
+            for k in (0, 1):
+                err = (outs["1"][p][k] - outs[other][p][k]).abs().max().item()
+                print("impl 1 vs %s %s geometry %d maxabs %.3e" % (other, p, k, err))
+                assert err < 2e-5
     # schedule 3 only changes how the weights reach shared memory: bit-identical results
     for p in ("bf16x3", "fp16f8", "bf16x1"):
-        assert torch.equal(outs["1"][p], outs["3"][p])
+        assert torch.equal(outs["1"][p][0], outs["3"][p][0]) and torch.equal(outs["1"][p][1], outs["3"][p][1])
+    # and every schedule agrees with the exact CUDA-core path on the ragged (dead-iteration) geometry
+    for impl in ("1", "2", "3"):
+        for p, tol in (("bf16x3", 3e-4), ("fp16f8", 1e-3)):
+            err = (outs[impl][p][1] - exact).abs().max().item()
+            print("impl %s %s vs fp32 path maxabs %.3e" % (impl, p, err))
+            assert err < tol
 
 
 def test_schedule_selection(S):
