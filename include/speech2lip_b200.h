@@ -114,6 +114,18 @@ int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, int32_t trans
                              const int64_t* frame_idx, float* latent, float* frame_bias,
                              int32_t n_frames, int32_t uv_dims, int32_t out_ch, void* stream);
 
+/* The per-frame-constant terms of rgb_forward alone (tf_nerf.py:254-258, 270-276, 427-442), for a caller that already
+ * holds AudioNet's output — the drop-in TalkingFace.rgb_forward receives it as the latent columns of uv_audio_pts
+ * (inference.py:150-158):  latent [F,64] with row stride latent_stride floats -> frame_bias [F,4,256] as above. */
+int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, int64_t latent_stride, const int64_t* frame_idx,
+                            float* frame_bias, int32_t n_frames, void* stream);
+
+/* flag[0] (device int32) <- 1 if any of the n_rows rows of x (row stride row_stride floats) differs bitwise from row 0 in
+ * columns [col0, col0+ncols), else 0.  Lets the drop-in detect inference.py's tiled inputs (inference.py:144: the same
+ * audio window H*W times; :151: the same latent in every row) and run them once / through the tensor-core path. */
+int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
+                        void* stream);
+
 /* Replaces: TalkingFace.rgb_forward (tf_nerf.py:225-285) for F frames x P points with a
  * per-frame-constant latent (frame_bias from s2l_audio_encode_fwd).  Point coordinates come from
  * geom->pts_mode.  raw_out [F*P_padless, out_ch] receives the raw linear outputs in point order. */

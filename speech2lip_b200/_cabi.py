@@ -42,6 +42,8 @@ SYMBOLS = {
     "s2l_pack_weights": (C.c_int32, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "s2l_audio_encode_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "s2l_latent_bias_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "s2l_rows_differ": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "s2l_mlp_fwd": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "s2l_rgb_forward_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,

@@ -34,7 +34,8 @@ __device__ __forceinline__ void conv_k3s2(const float* __restrict__ w, const flo
 __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __restrict__ blob, Layout L,
                                                            const float* __restrict__ audio, int transposed,
                                                            const long long* __restrict__ frame_idx,
-                                                           float* __restrict__ latent, float* __restrict__ frame_bias) {
+                                                           float* __restrict__ latent, float* __restrict__ frame_bias,
+                                                           const float* __restrict__ latent_in, long long latent_in_stride) {
   const float* A = reinterpret_cast<const float*>(blob + L.off_audio);
   const float* C = reinterpret_cast<const float*>(blob + L.off_const);
   const float* Fp = reinterpret_cast<const float*>(blob + L.off_fp32);
@@ -44,12 +45,6 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
   __shared__ float b0s[256], bss[256];
   const int f = blockIdx.x, tid = threadIdx.x;
 
-  const float* a = audio + (size_t)f * kAudioWin * kAudioFeat;
-  for (int i = tid; i < kAudioFeat * kAudioWin; i += 256) {
-    const int c = i / kAudioWin, t = i % kAudioWin;
-    // tf_nerf.py:203-207: [B,16,29] is permuted to [B,29,16]; a tensor whose last dim is 16 is used as is
-    x0[i] = transposed ? a[c * kAudioWin + t] : a[t * kAudioFeat + c];
-  }
   if (tid < 10) {
     float s = 0.f, c = 1.f;
     if (frame_idx) {
@@ -60,6 +55,17 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     }
     pe[2 * tid] = s;
     pe[2 * tid + 1] = c;
+  }
+  if (latent_in) {
+    // the caller already holds AudioNet's output (rgb_forward's latent columns): only the per-frame constants remain
+    if (tid < 64) lat[tid] = latent_in[(size_t)f * latent_in_stride + tid];
+    __syncthreads();
+  } else {
+  const float* a = audio + (size_t)f * kAudioWin * kAudioFeat;
+  for (int i = tid; i < kAudioFeat * kAudioWin; i += 256) {
+    const int c = i / kAudioWin, t = i % kAudioWin;
+    // tf_nerf.py:203-207: [B,16,29] is permuted to [B,29,16]; a tensor whose last dim is 16 is used as is
+    x0[i] = transposed ? a[c * kAudioWin + t] : a[t * kAudioFeat + c];
   }
   __syncthreads();
   conv_k3s2<29, 32, 16>(A + A_CONV0_W, A + A_CONV0_B, x0, x1, tid, 256);
@@ -84,6 +90,7 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     if (latent) latent[(size_t)f * kLatent + tid] = v;
   }
   __syncthreads();
+  }
   if (!frame_bias) return;
   {
     // bias0 = b_uv + (Wa a + b_a) + (Wt t + b_t)   (tf_nerf.py:252-258, same association order)
@@ -140,6 +147,45 @@ extern "C" int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, in
   if (n_frames == 0) return 0;
   audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed,
-      reinterpret_cast<const long long*>(frame_idx), latent, frame_bias);
+      reinterpret_cast<const long long*>(frame_idx), latent, frame_bias, nullptr, 0);
   return check_launch("audio_encode_kernel") ? 0 : 5;
+}
+
+extern "C" int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, int64_t latent_stride, const int64_t* frame_idx,
+                                       float* frame_bias, int32_t n_frames, void* stream) {
+  if (!blob || !latent || !frame_bias) { set_error("s2l_latent_bias_fwd: null blob/latent/frame_bias"); return 1; }
+  if (n_frames < 0 || latent_stride < 0) { set_error("s2l_latent_bias_fwd: negative n_frames/stride"); return 2; }
+  if (n_frames == 0) return 0;
+  audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(blob), blob_layout(), nullptr, 0, reinterpret_cast<const long long*>(frame_idx), nullptr,
+      frame_bias, latent, (long long)latent_stride);
+  return check_launch("audio_encode_kernel(latent)") ? 0 : 5;
+}
+
+namespace s2l {
+// flag[0] = 1 when any row differs (bitwise) from row 0 in columns [col0, col0 + ncols); the caller zeroes flag first
+__global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __restrict__ x, long long n_rows, long long row_stride,
+                                                          int col0, int ncols, int* __restrict__ flag) {
+  const long long total = n_rows * ncols;
+  bool diff = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ncols;
+    const int c = (int)(i - r * ncols);
+    diff |= x[r * row_stride + col0 + c] != x[col0 + c];
+  }
+  if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flag, 1);
+}
+}  // namespace s2l
+
+extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
+                                   void* stream) {
+  if (!x || !flag) { set_error("s2l_rows_differ: null x/flag"); return 1; }
+  if (n_rows < 0 || ncols < 0 || col0 < 0 || row_stride < col0 + ncols) { set_error("s2l_rows_differ: bad shape"); return 2; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+  if (n_rows <= 1 || ncols == 0) return 0;
+  const long long total = n_rows * ncols;
+  const int grid = (int)((total + 256 * 8 - 1) / (256 * 8) < 148 * 8 ? (total + 256 * 8 - 1) / (256 * 8) : 148 * 8);
+  rows_differ_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
+  return check_launch("rows_differ_kernel") ? 0 : 5;
 }

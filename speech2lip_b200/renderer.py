@@ -116,6 +116,36 @@ def rgb_forward_rows(w, x, time_idx=None):
     return out
 
 
+def rows_constant(x, col0, ncols):
+    """True when every row of the 2-D (or flattened-to-2-D) CUDA tensor x equals row 0 in columns [col0, col0+ncols)
+    (one small kernel + one host sync)."""
+    lib = _cabi.lib()
+    x = _f32c(x, "x")
+    x2 = x.reshape(x.shape[0], -1)
+    flag = torch.empty(1, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_rows_differ(_ptr(x2), x2.shape[0], x2.shape[1], int(col0), int(ncols), _ptr(flag), _stream()),
+                    "s2l_rows_differ")
+    return int(flag.item()) == 0
+
+
+def rgb_forward_const_latent(w, x, time_idx=None, precision="bf16x3"):
+    """TalkingFace.rgb_forward for the caller pattern of inference.py:144-158 — every row of x [N, uv_dims+64] carries
+    the SAME latent (checked by the caller): per-frame constants from row 0's latent, then the fused tensor-core MLP
+    on the N explicit points."""
+    lib = _cabi.lib()
+    x = _f32c(x, "uv_audio_pts")
+    N = x.shape[0]
+    bias = torch.empty(1, 4, 256, device=x.device)
+    idx = None if time_idx is None else torch.tensor([int(time_idx)], dtype=torch.int64, device=x.device)
+    lat0 = x[0, w.uv_dims:]                                    # view: 64 contiguous floats
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_latent_bias_fwd(_ptr(w.blob), _ptr(lat0), 64, _ptr(idx), _ptr(bias), 1, _stream()),
+                    "s2l_latent_bias_fwd")
+    pts = x[:, :w.uv_dims].contiguous().view(1, N, w.uv_dims)
+    return mlp_points(w, bias, pts, precision)[0]
+
+
 def mlp_points(w, frame_bias, pts, precision="bf16x3"):
     """rgb_forward on explicit points with per-frame-constant latent: pts [F,P,uv_dims] -> raw [F,P,out_ch]."""
     lib = _cabi.lib()

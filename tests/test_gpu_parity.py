@@ -345,6 +345,63 @@ def test_talking_face_drop_in(S, golden):
     assert maxabs((rgb[0] - 1.0).cpu(), g["rgb"]) < PARITY_TOL
 
 
+def test_talking_face_drop_in_fast_path(S):
+    """inference.py:144-158 verbatim at a size where the drop-in recognises the tiled inputs: the audio window is encoded
+    once, the constant-latent rows go through the tensor-core MLP; a single differing row must fall back to the general
+    per-row path (bit-identical to it)."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval").to(dev()).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming").items()}, strict=False)
+    H, W = 40, 56
+    win = torch.from_numpy(synth.make_audio(1, seed=11)).to(dev())
+    coords = torch.from_numpy(O.get_coords(W, H).numpy()).to(dev())
+    t = torch.tensor([7], device=dev())
+
+    def run():
+        with torch.no_grad():
+            audio = win.tile(H * W, 1, 1)                                             # inference.py:144
+            ab = m.audio_merge_forward(audio)
+            x = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, 66)      # :151, :158
+            return ab, x, m.rgb_forward(x, time_pts=t, rgb_pts=None)
+
+    m.dropin_fast_path = False
+    ab_g, x_g, out_g = run()
+    m.dropin_fast_path = True
+    for prec in ("bf16x3", "fp16f8"):
+        m.dropin_precision = prec
+        ab_f, x_f, out_f = run()
+        assert ab_f.shape == ab_g.shape and torch.equal(ab_f, ab_g)              # AudioNet: bit-invariant to tiling
+        err = maxabs(out_f.cpu(), out_g.cpu())
+        print("drop-in fast path %s vs general fp32 path: %.2e" % (prec, err))
+        assert out_f.shape == out_g.shape and err < PARITY_TOL
+    # the in-kernel uv grid is torch.linspace bit for bit (ATen fuses end - step*k into one FMA), so the batched renderer
+    # (coordinates synthesised in the kernel) and the drop-in (coordinates from the caller's get_coords) agree exactly
+    m.dropin_precision = "bf16x3"
+    _, _, out_b = run()
+    with torch.no_grad():
+        rgb = m.renderer("bf16x3").render_frames(win, torch.tensor([7]), H, W)[0].reshape(-1, 3)
+        rgb256 = m.renderer("bf16x3").render_frames(win, torch.tensor([7]), 256, 256)[0].reshape(-1, 3)
+        c256 = torch.from_numpy(O.get_coords(256, 256).numpy()).to(dev())
+        lat1 = m.audio_merge_forward(win)
+        x256 = torch.cat([c256, lat1.expand(256 * 256, -1)], -1).contiguous()
+        out256 = m.rgb_forward(x256, time_pts=t)
+    assert torch.equal(out_b, rgb) and torch.equal(out256, rgb256)
+    # one row with a different latent: not the tiled pattern -> general path, bit-identical to it
+    x2 = x_g.clone()
+    x2[5, 2 + 3] += 1.0
+    with torch.no_grad():
+        o_fast_on = m.rgb_forward(x2, time_pts=t)
+        m.dropin_fast_path = False
+        o_general = m.rgb_forward(x2, time_pts=t)
+    assert torch.equal(o_fast_on, o_general)
+    # and against the oracle (CPU restatement of the reference) on a sample of rows
+    sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming"))
+    rows = torch.arange(0, H * W, 97)
+    with torch.no_grad():
+        want = O.rgb_forward(sd, x_g[rows].cpu(), torch.tensor([7]))
+    assert maxabs(out_f[rows].cpu(), want) < PARITY_TOL
+
+
 # ------------------------------------------------------------------------------------------ next row: post-fusion compose
 @pytest.mark.parametrize("case", ["pf_a", "pf_b"])
 def test_post_fusion_compose_vs_golden(S, golden, case):
