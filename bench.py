@@ -339,6 +339,36 @@ def run_gpu_arm(a):
                     extras["live_%s_%dx%d_%s" % (mode_l, H, W, prec_l)] = {"frames_per_s": FL / (ms * 1e-3), "ms_per_step": ms,
                                                                           "frames_per_step": FL}
 
+        # the UNMODIFIED caller: inference.py:144-159 verbatim through the TalkingFace drop-in, one frame per iteration
+        # (tile the window H*W times, audio_merge_forward, cat with the uv grid, rgb_forward)
+        try:
+            cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+            tf = s2l.TalkingFace(device=dev, cfg=cfg, mode="eval").to(dev).eval()
+            tf.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming", 2, 3).items()}, strict=False)
+            wins = torch.from_numpy(synth.make_audio(32, seed=9)).to(dev)
+            vv, uu = torch.meshgrid(torch.linspace(0.0, 1.0, H, device=dev), torch.linspace(0.0, 1.0, W, device=dev), indexing="ij")
+            coords = torch.stack([uu, vv], -1).view(-1, 2)                   # the caller's get_coords (rendering.py:9-28)
+
+            def dropin_frame(i):
+                with torch.no_grad():
+                    au = wins[i:i + 1].tile(H * W, 1, 1)
+                    ab = tf.audio_merge_forward(au)
+                    xx = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, tf.audio_dims + 2)
+                    return tf.rgb_forward(xx, time_pts=torch.tensor([i], device=dev), rgb_pts=None)[:, :3]
+            for i in range(3):
+                dropin_frame(i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(32):
+                dropin_frame(i)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            extras["drop_in_inference_loop_%dx%d" % (H, W)] = {"frames_per_s": 32 / dt, "ms_per_step": dt / 32 * 1e3, "frames_per_step": 1,
+                                                              "precision": tf.dropin_precision,
+                                                              "what": "inference.py:144-159 call sequence through TalkingFace, wall clock incl. Python"}
+        except Exception as e:      # an extra must never take the headline line down
+            extras["drop_in_inference_loop"] = {"error": str(e)[:200], "frames_per_s": 0.0, "ms_per_step": 0.0}
+
     t = torch.tensor([dev_ms, e2e_ms, ker_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
