@@ -222,7 +222,7 @@ class TalkingFace(nn.Module):
                 and R.rows_constant(audio, 0, audio.shape[1] * audio.shape[2])):
             # inference.py:144 tiles ONE window H*W times: encode it once (AudioNet is bit-invariant to batch tiling)
             latent, _ = R.audio_encode(self.packed_weights(), audio[:1], None, want_latent=True, want_bias=False)
-            return latent.expand(audio.shape[0], -1)
+            return latent.expand(audio.shape[0], -1).contiguous()      # a fresh, ordinarily-strided [B,64] like the reference's
         latent, _ = R.audio_encode(self.packed_weights(), audio, None, want_latent=True, want_bias=False)
         return latent
 
