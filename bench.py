@@ -186,7 +186,7 @@ def run_gpu_arm(a):
     import speech2lip_b200 as s2l
     from speech2lip_b200 import _cabi, renderer as R
     from speech2lip_b200.dist import broadcast_params
-    from oracle import synth            # synthetic weights/inputs only (no oracle compute on this path)
+    from speech2lip_b200 import synth   # synthetic weights/inputs (generators only; nothing from oracle/ on this path)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -11,7 +11,7 @@ if len(sys.argv) > 1 and sys.argv[1] != "--child":
 sys.path.insert(0, ROOT)
 import torch
 import speech2lip_b200 as s2l
-from oracle import synth
+from speech2lip_b200 import synth
 dev = torch.device("cuda:0")
 sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
 w = s2l.PackedWeights(sd)

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import speech2lip_b200 as s2l
 from speech2lip_b200 import _cabi
-from oracle import synth
+from speech2lip_b200 import synth
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 dev = torch.device("cuda:0")
 sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
