@@ -18,6 +18,23 @@ def param_order():
     return [n + s for n in _W_ORDER for s in (".weight", ".bias")]
 
 
+def _wgrad(dy, h):
+    """sum_n dy[l,n,:]^T h[l,n,:] for a stack of layers: [L,N,A] x [L,N,B] -> [L,A,B].  A [256,N] x [N,256] product has only
+    four 128x128 output tiles — far too few for 148 SMs — so the reduction over N is split into S slabs that run as
+    extra batch entries of ONE bmm and are summed afterwards (split-K, deterministic)."""
+    L, N = dy.shape[0], dy.shape[1]
+    S = max(1, min(16, N // 512))
+    n_main = (N // S) * S
+    if S == 1 or n_main == 0:
+        return torch.bmm(dy.transpose(1, 2), h)
+    a = dy[:, :n_main].reshape(L * S, n_main // S, dy.shape[2])
+    b = h[:, :n_main].reshape(L * S, n_main // S, h.shape[2])
+    out = torch.bmm(a.transpose(1, 2), b).view(L, S, dy.shape[2], h.shape[2]).sum(1)
+    if n_main < N:
+        out = out + torch.bmm(dy[:, n_main:].transpose(1, 2), h[:, n_main:])
+    return out
+
+
 class FusedMLPRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, time_idx, packed, div_term, *params):
@@ -56,21 +73,29 @@ class FusedMLPRows(torch.autograd.Function):
         lat = x[:, D:]
         g = {}
         # ---- weight gradients: plain GEMMs over the saved / produced [N,256] buffers
-        g["output_linear.weight"] = d_out.t() @ acts[9]
+        g["output_linear.weight"] = _wgrad(d_out[None], acts[9:10])[0]
         g["output_linear.bias"] = d_out.sum(0)
-        dpre = {0: dsave[1], 1: dsave[2], 2: dsave[3], 3: dsave[4], 4: dsave[5], 5: dsave[7], 6: dsave[8], 7: dsave[9]}
-        h_in = {0: acts[0], 1: acts[1], 2: acts[2], 3: acts[3], 4: acts[4], 6: acts[7], 7: acts[8]}
-        for l in range(8):
-            if l == 5:
-                g["pts_linears.5.weight"] = torch.cat([dpre[5].t() @ acts[6], dpre[5].t() @ acts[5]], 1)   # [h_skip | h4]
-            else:
-                g["pts_linears.%d.weight" % l] = dpre[l].t() @ h_in[l]
-            g["pts_linears.%d.bias" % l] = dpre[l].sum(0)
-        s_net, s_skip = d_net.sum(0), d_skip.sum(0)
-        g["fc_uv.weight"] = d_net.t() @ pe
-        g["fc_uv_skip.weight"] = d_skip.t() @ pe
-        g["fc_audio.weight"] = d_net.t() @ lat
-        g["fc_audio_skip.weight"] = d_skip.t() @ lat
+        # dsave rows: 0 d_net, 1-5 dPre of layers 0-4, 6 d_skip, 7-9 dPre of layers 5-7;  acts rows: 0-4 inputs of layers 0-4,
+        # 5 h4 / 6 h_skip (the two halves of layer 5's input), 7-8 inputs of layers 6-7, 9 input of output_linear.
+        # Same-shape products are batched (the step is launch-bound at the reference's 9 600-row calls).
+        col = dsave.sum(1)                                                   # every bias gradient in one reduction [10,256]
+        w04 = _wgrad(dsave[1:6], acts[0:5])                                  # layers 0-4
+        w67 = _wgrad(dsave[8:10], acts[7:9])                                 # layers 6-7
+        w5 = _wgrad(dsave[7:8].expand(2, -1, -1), torch.stack([acts[6], acts[5]]))   # [h_skip | h4]
+        for l in range(5):
+            g["pts_linears.%d.weight" % l] = w04[l]
+            g["pts_linears.%d.bias" % l] = col[1 + l]
+        g["pts_linears.5.weight"] = torch.cat([w5[0], w5[1]], 1)
+        g["pts_linears.5.bias"] = col[7]
+        for i, l in enumerate((6, 7)):
+            g["pts_linears.%d.weight" % l] = w67[i]
+            g["pts_linears.%d.bias" % l] = col[8 + i]
+        s_net, s_skip = col[0], col[6]
+        both = torch.stack([d_net, d_skip])                                  # [2,N,256]
+        wuv = _wgrad(both, pe[None].expand(2, -1, -1))                       # fc_uv / fc_uv_skip
+        wau = _wgrad(both, lat[None].expand(2, -1, -1))                      # fc_audio / fc_audio_skip
+        g["fc_uv.weight"], g["fc_uv_skip.weight"] = wuv[0], wuv[1]
+        g["fc_audio.weight"], g["fc_audio_skip.weight"] = wau[0], wau[1]
         for n, s in (("fc_uv", s_net), ("fc_audio", s_net), ("fc_uv_skip", s_skip), ("fc_audio_skip", s_skip)):
             g[n + ".bias"] = s
         if ctx.time_idx is not None:
