@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_cl(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cl(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (clock64() - t0 > kWatchdogCycles) __trap();
   }
 }
 // cta_group::2 MMAs (issued by the leader CTA only) and the commit that signals both CTAs

@@ -185,7 +185,10 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-// Bounded mbarrier wait: a protocol bug must surface as a trapped kernel, never as a hung GPU box.
+// Bounded mbarrier wait: a protocol bug must surface as a trapped kernel, never as a hung GPU box.  The bound is generous
+// (~30 s of SM clocks; a launch lasts ~0.1 s): a kernel slowed 100x by compute-sanitizer, or time-sliced against another
+// process, must not be mistaken for a deadlock.
+constexpr long long kWatchdogCycles = 60000000000ll;
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
 #ifdef S2L_DBG_SUSPEND       // experiment: let the hardware park the warp (up to ~20 us) instead of polling
@@ -195,7 +198,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (BACKOFF) __nanosleep(128);     // roles that run ahead (producers) must not steal issue slots while they wait
-    if (clock64() - t0 > 4000000000ll) {
+    if (clock64() - t0 > kWatchdogCycles) {
       printf("s2l tc kernel: mbarrier wait timeout (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x,
              threadIdx.x, parity);
       __trap();
@@ -209,7 +212,7 @@ __device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (clock64() - t0 > kWatchdogCycles) __trap();
   }
 }
 
