@@ -119,3 +119,33 @@ def test_training_mode_audionet_matches_oracle_on_cpu():
     ref = O.audio_merge_forward(O.to_torch_sd(sd), a)
     assert (m.audio_merge_forward(a) - ref).abs().max().item() < 1e-6
     assert (m.audio_merge_forward(a.permute(0, 2, 1).contiguous()) - ref).abs().max().item() < 1e-6
+
+
+def test_split_k_weight_gradient_helper_cpu():
+    """autograd._wgrad (split-K batched dW = dY^T H) equals the plain batched product for ragged N, including the
+    expanded (stride-0) operands the backward passes in."""
+    from speech2lip_b200.autograd import _wgrad
+    g = torch.Generator().manual_seed(0)
+    for N in (7, 512, 1023, 9600, 9601):
+        dy = torch.randn(3, N, 40, generator=g, dtype=torch.float64)
+        h = torch.randn(3, N, 24, generator=g, dtype=torch.float64)
+        ref = torch.bmm(dy.transpose(1, 2), h)
+        assert (_wgrad(dy, h) - ref).abs().max().item() < 1e-10
+        e = _wgrad(dy[:1].expand(3, -1, -1), h)
+        assert (e - torch.bmm(dy[:1].expand(3, -1, -1).transpose(1, 2), h)).abs().max().item() < 1e-10
+
+
+def test_synth_generators_are_shared_not_duplicated():
+    """bench.py's product arm imports the synthetic generators from the package; oracle/synth.py is only a shim."""
+    from oracle import synth as a
+    from speech2lip_b200 import synth as b
+    assert a.make_state_dict is b.make_state_dict and a.make_audio is b.make_audio
+    # ... and the only place bench.py touches oracle/ is the CPU-baseline / reference-arm sampler
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                assert fn.name == "cpu_sample", "bench.py imports oracle/ in %s()" % fn.name
+    for node in tree.body:
+        assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node)), "module-level oracle import"
