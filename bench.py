@@ -339,6 +339,23 @@ def run_gpu_arm(a):
                     extras["live_%s_%dx%d_%s" % (mode_l, H, W, prec_l)] = {"frames_per_s": FL / (ms * 1e-3), "ms_per_step": ms,
                                                                           "frames_per_step": FL}
 
+        if vol:
+            # live sequence HOST -> HOST: pinned windows in, uint8 BGR frames out (what inference.py:173-178 writes), D2H of chunk i
+            # under the render of chunk i+1 (LipRenderer.render_sequence_host)
+            Ts = 512
+            ah = torch.from_numpy(synth.make_audio(Ts, seed=11)).pin_memory()
+            ih = torch.arange(Ts).pin_memory()
+            oh = torch.empty(Ts, H, W, 3, dtype=torch.uint8, pin_memory=True)
+            rs = s2l.LipRenderer(wL, a.precision)
+            rs.render_sequence_host(ah, ih, H, W, 64, "bgr8", oh)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rs.render_sequence_host(ah, ih, H, W, 64, "bgr8", oh)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            extras["live_sequence_host_to_host_bgr8_%dx%d_%s" % (H, W, a.precision)] = {
+                "frames_per_s": Ts / dt, "ms_per_step": dt / (Ts / 64) * 1e3, "frames_per_step": 64,
+                "d2h_bytes_per_step": 64 * H * W * 3, "what": "512 frames, pinned host windows -> uint8 BGR host frames, wall clock"}
         # the UNMODIFIED caller: inference.py:144-159 verbatim through the TalkingFace drop-in, one frame per iteration
         # (tile the window H*W times, audio_merge_forward, cat with the uv grid, rgb_forward)
         try:

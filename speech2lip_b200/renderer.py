@@ -225,13 +225,16 @@ def audio_windows(logits):
     return out
 
 
-def frames_to_bgr8(rgb):
+def frames_to_bgr8(rgb, out=None):
     """inference.py:173-178 output staging: [...,3] fp32 RGB -> uint8 BGR exactly as cv2.imwrite(img * 255) stores it."""
     lib = _cabi.lib()
     x = _f32c(rgb, "rgb")
     if x.shape[-1] != 3:
         raise ValueError("rgb must have 3 channels last")
-    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    elif out.dtype != torch.uint8 or tuple(out.shape) != tuple(x.shape) or not out.is_contiguous() or out.device != x.device:
+        raise ValueError("out must be a contiguous uint8 tensor of rgb's shape on rgb's device")
     with torch.cuda.device(x.device):
         _cabi.check(lib.s2l_frames_to_bgr8(_ptr(x), x.numel() // 3, _ptr(out), _stream()), "s2l_frames_to_bgr8")
     return out
@@ -343,6 +346,50 @@ class LipRenderer:
         T = audio_window.shape[0]
         idx = torch.clamp(torch.arange(T, device=audio_window.device) + int(index), max=int(total_frame) - 1)
         return self.render_frames(audio_window, idx, H, W, mode="ensemble4", eps_shift=torch.as_tensor(eps_shift))
+
+    def render_sequence_host(self, audio_host, index_host, H, W, frames_per_step=64, out="bgr8", out_host=None, **kw):
+        """Streams a whole T-frame sequence HOST -> HOST (the per-frame staging around the path):
+        per chunk of `frames_per_step` frames  H2D (windows, indices) -> render -> [uint8 BGR staging, exactly the bytes
+        cv2.imwrite(img * 255) stores, inference.py:173-178] -> D2H,  with the D2H of chunk i on a copy stream while chunk
+        i+1 renders (double-buffered device outputs).  audio_host [T,16,29] / index_host [T] should be pinned;
+        returns out_host [T,H,W,3] (uint8 BGR for out="bgr8", fp32 RGB for out="rgb32"), pinned if allocated here."""
+        if out not in ("bgr8", "rgb32"):
+            raise ValueError("out must be 'bgr8' or 'rgb32'")
+        dev = self.w.device
+        T = audio_host.shape[0]
+        Fs = max(1, min(int(frames_per_step), max(T, 1)))
+        dt = torch.uint8 if out == "bgr8" else torch.float32
+        if out_host is None:
+            out_host = torch.empty((T, H, W, 3), dtype=dt, pin_memory=True)
+        elif tuple(out_host.shape) != (T, H, W, 3) or out_host.dtype != dt or out_host.is_cuda:
+            raise ValueError("out_host must be a host %s tensor [T,H,W,3]" % dt)
+        if T == 0:
+            return out_host
+        key = (Fs, H, W, out, dev)
+        st = self.__dict__.get("_seq_state")
+        if st is None or st["key"] != key:
+            st = {"key": key, "copy": torch.cuda.Stream(dev),
+                  "rgb": [torch.empty(Fs, H, W, 3, device=dev) for _ in range(2)],
+                  "u8": [torch.empty(Fs, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)] if out == "bgr8" else None,
+                  "rendered": [torch.cuda.Event() for _ in range(2)], "copied": [torch.cuda.Event() for _ in range(2)]}
+            self._seq_state = st
+        compute = torch.cuda.current_stream(dev)
+        for b in range(2):
+            st["copied"][b].record(compute)                  # nothing in flight on the buffers yet
+        for c, s0 in enumerate(range(0, T, Fs)):
+            n, b = min(Fs, T - s0), c & 1
+            compute.wait_event(st["copied"][b])              # the D2H that last read buffer b has finished
+            a = audio_host[s0:s0 + n].to(dev, non_blocking=True)
+            i = index_host[s0:s0 + n].to(dev, non_blocking=True)
+            rgb = self.render_frames(a, i, H, W, out=st["rgb"][b][:n], **kw)
+            src = frames_to_bgr8(rgb, out=st["u8"][b][:n]) if out == "bgr8" else rgb
+            st["rendered"][b].record(compute)
+            with torch.cuda.stream(st["copy"]):
+                st["copy"].wait_event(st["rendered"][b])
+                out_host[s0:s0 + n].copy_(src, non_blocking=True)
+                st["copied"][b].record(st["copy"])
+        st["copy"].synchronize()
+        return out_host
 
     def render_frames_host(self, audio_host, index_host, H, W, out_host=None, **kw):
         """End-to-end call on HOST buffers: H2D of the audio windows / indices (pinned -> async), render,

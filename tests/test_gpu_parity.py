@@ -612,3 +612,23 @@ def test_sync_window_render_vs_oracle(S, precision):
     print("sync window %s maxabs %.3e" % (precision, err))
     assert err < (3e-4 if precision == "fp32" else PARITY_TOL)
     assert not torch.equal(got[3], got[4])                  # same index, different audio window and eps
+
+
+def test_render_sequence_host_pipeline(S):
+    """the pipelined host->host sequence renderer (D2H of chunk i under the render of chunk i+1,
+    uint8 BGR staging on the GPU) returns exactly the frames of a plain render_frames + frames_to_bgr8, ragged tail included."""
+    sd = {k: torch.from_numpy(v).to(dev()) for k, v in synth.make_state_dict(0, "kaiming").items()}
+    r = S.LipRenderer(S.PackedWeights(sd), "bf16x3")
+    T, H, W = 150, 40, 56
+    audio_h = torch.from_numpy(synth.make_audio(T, seed=21)).pin_memory()
+    index_h = torch.arange(100, 100 + T).pin_memory()
+    want = r.render_frames(audio_h.to(dev()), index_h.to(dev()), H, W)
+    want_u8 = S.frames_to_bgr8(want).cpu()
+    for _ in range(2):                                            # second pass reuses the cached streams / buffers
+        got_u8 = r.render_sequence_host(audio_h, index_h, H, W, frames_per_step=64, out="bgr8")
+        assert got_u8.dtype == torch.uint8 and got_u8.is_pinned() and torch.equal(got_u8, want_u8)
+    got32 = r.render_sequence_host(audio_h, index_h, H, W, frames_per_step=37, out="rgb32")
+    assert torch.equal(got32, want.cpu())
+    ens = r.render_sequence_host(audio_h[:5], index_h[:5], H, W, frames_per_step=2, out="rgb32", mode="ensemble4", eps_shift=0.002)
+    assert torch.equal(ens, r.render_frames(audio_h[:5].to(dev()), index_h[:5].to(dev()), H, W, mode="ensemble4", eps_shift=0.002).cpu())
+    assert r.render_sequence_host(audio_h[:0], index_h[:0], H, W).shape == (0, H, W, 3)
