@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // The whole warp walks the layer program in lock step, so every address / descriptor is computed on the uniform
     // datapath; one elected lane issues the tcgen05 instructions.  The program is STATIC: ring stage, operand offsets
     // and instruction descriptors of every MMA are compile-time constants relative to a few per-tile bases (the ring
-    // has 4 stages and every layer uses a multiple of... 2/8/10/8/4 granules, so the stage at each program point is
+    // has 4 stages and the layers use 2 / 8 / 10 / 8 / 4 granules, so the stage at each program point is
     // fixed: G0 starts at 0, G1-4 at 2, G5 at 2, G6-7 at 0, G8 at 0), which brings the issue cost per MMA well under
     // the 64 tensor-pipe cycles it covers — the issuing thread must run AHEAD of the pipe (queue depth ~7 MMAs).
     uint32_t ph = 0;                            // bit s = parity to wait for on b_full[s]
@@ -259,8 +259,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       epi_par ^= 1u << hk;
     };
     using std::integral_constant;
-    auto I = [](auto v) { return v; };
-    (void)I;
 #define S2L_IC(v) integral_constant<int, (v)>{}
 #define S2L_BC(v) integral_constant<bool, (v)>{}
     // hidden layer (4 K-chunks per accumulator half), ring position START at entry
