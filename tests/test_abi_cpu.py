@@ -149,3 +149,21 @@ def test_synth_generators_are_shared_not_duplicated():
                 assert fn.name == "cpu_sample", "bench.py imports oracle/ in %s()" % fn.name
     for node in tree.body:
         assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node)), "module-level oracle import"
+
+
+def test_bench_constants_and_traffic_helper_cpu():
+    """bench.py's roofline inputs: the algorithmic FLOP counts of SURVEY 8(d), the issued-MAC count of the folded program and
+    the ncu-measured DRAM traffic scaled to a launch."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("s2l_bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    # 2 x (fc_uv 63*256 + fc_uv_skip 63*256 + 5*256^2 + 512*256 + 2*256^2 + 256*4) for V, 42-wide PE / 3 outputs for L
+    assert b.FLOP_PER_POINT["volumetric"] == 2 * (2 * 63 * 256 + 5 * 256 * 256 + 512 * 256 + 2 * 256 * 256 + 256 * 4)
+    assert b.FLOP_PER_POINT["plain"] == 2 * (2 * 42 * 256 + 5 * 256 * 256 + 512 * 256 + 2 * 256 * 256 + 256 * 3)
+    # folded program: G0 64x256, G1-4, G5 (64+256)x256, G6-7, G8 256x16
+    assert b.ISSUED_MAC_PER_POINT == 64 * 256 + 4 * 256 * 256 + 320 * 256 + 2 * 256 * 256 + 256 * 16
+    t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    one = b.ncu_traffic(t["frames_per_launch"], t["points_per_launch"])
+    assert one == t["dram_bytes_read"] + t["dram_bytes_write"]
+    assert abs(b.ncu_traffic(8, t["points_per_launch"]) - 8 * one) < 1e-6 * one
