@@ -632,3 +632,28 @@ def test_render_sequence_host_pipeline(S):
     ens = r.render_sequence_host(audio_h[:5], index_h[:5], H, W, frames_per_step=2, out="rgb32", mode="ensemble4", eps_shift=0.002)
     assert torch.equal(ens, r.render_frames(audio_h[:5].to(dev()), index_h[:5].to(dev()), H, W, mode="ensemble4", eps_shift=0.002).cpu())
     assert r.render_sequence_host(audio_h[:0], index_h[:0], H, W).shape == (0, H, W, 3)
+
+
+def test_talking_face_drop_in_fast_path_volumetric_module(S):
+    """the constant-latent fast path on the Mode-V module (uv_dims=3, output_ch=4): rows [N, 3+64] through the tensor-core
+    MLP vs the general per-row fp32 path and vs the oracle."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval", uv_dims=3, output_ch=4).to(dev()).eval()
+    sd_np = synth.make_state_dict(0, "kaiming", 3, 4)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()}, strict=False)
+    N = 3000
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand(N, 3, generator=g).to(dev())
+    win = torch.from_numpy(synth.make_audio(1, seed=4)).to(dev())
+    t = torch.tensor([11], device=dev())
+    with torch.no_grad():
+        lat = m.audio_merge_forward(win.tile(N, 1, 1))
+        x = torch.cat([pts, lat], -1)
+        m.dropin_fast_path = False
+        general = m.rgb_forward(x, time_pts=t)
+        m.dropin_fast_path = True
+        fast = m.rgb_forward(x, time_pts=t)
+        want = O.rgb_forward(O.to_torch_sd(sd_np), x[::29].cpu(), torch.tensor([11]), uv_dims=3)
+    assert fast.shape == (N, 4) and maxabs(fast.cpu(), general.cpu()) < PARITY_TOL
+    assert not torch.equal(fast, general)                       # it really took the other kernel
+    assert maxabs(fast[::29].cpu(), want) < PARITY_TOL
