@@ -493,12 +493,16 @@ int launch_mlp_tc2(const TcArgs& a, long long n_tiles, int npass, cudaStream_t s
 // kernel (in the sustained, power-capped regime it halves the L2 -> SMEM weight bytes per SM: +6 % SM clock, +2.5-3 %
 // frames/s, round-1e measurements) and small launches the single-CTA kernel (shorter dependency chains: ~4 % faster in
 // short bursts).
-int tc_impl_for(long long n_tiles) {
+static int tc_forced() {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("S2L_TC_IMPL");
     forced = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
   }
+  return forced;
+}
+int tc_impl_for(long long n_tiles) {
+  const int forced = tc_forced();
   if (forced) return forced;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -526,7 +530,13 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   if (n_tiles == 0) return 0;
   if (src.uv_dims != 2 && src.uv_dims != 3) { set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims); return 2; }
   const int impl = tc_impl_for(n_tiles);
-  if (impl == 2) return launch_mlp_tc2(a, n_tiles, npass, st);
+  if (impl == 2) {
+    const int r = launch_mlp_tc2(a, n_tiles, npass, st);
+    if (r == 0 || tc_forced()) return r;
+    // the automatically chosen pair schedule is unavailable here (no tensor-map encoder in the driver, a partition
+    // that cannot co-schedule 2-CTA clusters, ...): same arithmetic on independent CTAs — still this library's kernel
+    cudaGetLastError();
+  }
   if (impl == 3) return launch_tc_cl<2>(a, n_tiles, npass, src.uv_dims, st);
   return launch_tc_cl<1>(a, n_tiles, npass, src.uv_dims, st);
 }
