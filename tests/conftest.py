@@ -18,7 +18,7 @@ def golden():
     """tests/golden/reference_golden.npz -> {case: {key: ndarray}} (outputs of the REAL
     reference, produced by tests/golden/make_golden.py in the build container)."""
     cases = {}
-    for fn in ("reference_golden.npz", "reference_golden_postfusion.npz", "reference_golden_staging.npz"):
+    for fn in ("reference_golden.npz", "reference_golden_postfusion.npz", "reference_golden_staging.npz", "reference_golden_grid.npz"):
         z = np.load(os.path.join(ROOT, "tests", "golden", fn))
         for k in z.files:
             c, name = k.split("/", 1)

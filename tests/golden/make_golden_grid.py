@@ -1,0 +1,36 @@
+"""Generates tests/golden/reference_golden_grid.npz by running the REAL reference (build container only, needs
+/root/reference):  python tests/golden/make_golden_grid.py
+
+One wide plain render (inference.py:144-159 as written, 40 x 256, kaiming weights) whose uv grid contains the columns on
+which a two-rounding linspace differs from torch.linspace by 1 ulp — after the 2^9 positional-encoding frequency that is
+~1e-4 at the output, so this case pins the in-kernel grid to ATen's fused form at a tolerance the other (narrow) cases
+cannot."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import synth                      # noqa: E402
+from oracle.ref_shim import load_reference    # noqa: E402
+from make_golden import ref_model             # noqa: E402
+
+ns = load_reference()
+torch.set_num_threads(8)
+sd = synth.make_state_dict(seed=0, kind="kaiming", uv_dims=2, output_ch=3)
+m = ref_model(ns, sd, 2, 3)
+audio = torch.from_numpy(synth.make_audio(4, seed=1))
+H, W, idx = 40, 256, 7
+with torch.no_grad():
+    a = audio[2:3].tile(H * W, 1, 1)
+    coords = ns.get_coords(W, H, torch.device("cpu"))
+    ab = m.audio_merge_forward(a)
+    x = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, 66)
+    out = m.rgb_forward(x, time_pts=torch.tensor([idx]), rgb_pts=None)
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden_grid.npz"),
+                    **{"grid_kaiming_40x256_i7/audio": audio[2:3].numpy(), "grid_kaiming_40x256_i7/index": np.int64(idx),
+                       "grid_kaiming_40x256_i7/coords": coords.numpy(),
+                       "grid_kaiming_40x256_i7/rgb": out[:, :3].reshape(H, W, 3).numpy()})
+print("wrote reference_golden_grid.npz", out.shape, float(out.abs().max()))

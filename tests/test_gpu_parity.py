@@ -657,3 +657,15 @@ def test_talking_face_drop_in_fast_path_volumetric_module(S):
     assert fast.shape == (N, 4) and maxabs(fast.cpu(), general.cpu()) < PARITY_TOL
     assert not torch.equal(fast, general)                       # it really took the other kernel
     assert maxabs(fast[::29].cpu(), want) < PARITY_TOL
+
+
+def test_wide_grid_vs_golden(S, golden):
+    """a 40 x 256 plain render from the REAL reference: the exact path must land within 2e-5 (a two-rounding uv grid is
+    ~1e-4 off on this case), the parity modes within the 1e-3 bar."""
+    g = golden["grid_kaiming_40x256_i7"]
+    for precision, tol in (("fp32", 1.5e-5), ("bf16x3", 3e-4), ("fp16f8", PARITY_TOL)):
+        r = S.LipRenderer(packed(S, "kaiming"), precision)
+        rgb = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([int(g["index"])]), 40, 256)
+        err = maxabs(rgb[0].cpu(), g["rgb"])
+        print("wide grid %s maxabs %.3e" % (precision, err))
+        assert err < tol

@@ -128,3 +128,24 @@ def test_staging_formats(golden):
     assert w["windows"].shape == (12, 16, 29)
     u = golden["u8"]
     np.testing.assert_array_equal(O.frames_to_bgr8(u["rgb"]).numpy(), u["bgr8"])
+
+
+def test_wide_grid_case_pins_the_fused_linspace(golden):
+    """get_coords at W = 256 against the REAL reference: torch.linspace's upper half is end - step*k in ONE fused
+    multiply-add; the two-rounding form is 1 ulp off in ~9 % of the columns (the bug the in-kernel grid had), which this
+    case would expose (the narrow golden cases cannot).  Also: the oracle reproduces the reference's wide render."""
+    g = golden["grid_kaiming_40x256_i7"]
+    coords = O.get_coords(256, 40).numpy()
+    assert np.array_equal(coords, g["coords"])
+    n = 256
+    step = np.float32(1.0) / np.float32(n - 1)
+    i = np.arange(n)
+    k = (n - 1 - i).astype(np.float32)
+    fused = np.where(i < n // 2, (step * i.astype(np.float32)).astype(np.float32), (1.0 - np.float64(step) * k).astype(np.float32))
+    two = np.where(i < n // 2, fused, (np.float32(1.0) - (step * k).astype(np.float32)).astype(np.float32))
+    u = g["coords"].reshape(40, 256, 2)[0, :, 0]
+    assert np.array_equal(u, fused) and int((u != two).sum()) >= 10
+    sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming"))
+    with torch.no_grad():
+        rgb = O.render_plain(sd, torch.from_numpy(g["audio"]), int(g["index"]), 40, 256)
+    assert np.abs(rgb.numpy() - g["rgb"]).max() < 2e-5
