@@ -29,8 +29,22 @@ with torch.no_grad():
     ab = m.audio_merge_forward(a)
     x = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, 66)
     out = m.rgb_forward(x, time_pts=torch.tensor([idx]), rgb_pts=None)
+# the same width through the real 4-tap local ensemble (Trainer.predict_lip_image, training.py:158-251), RNG-aligned eps
+H2, W2, idx2, seed = 12, 256, 9, 13
+tr = ns.Trainer(m, None, torch.device("cpu"), "/tmp", cfg=ns.cfg, batch_rays=H2 * W2, use_audio_net=True, use_time=True,
+                use_audio=True, use_perceptual_loss=False, use_syncloss=False, multi_gpu=False)
+tr.height, tr.width = H2, W2
+coords2 = ns.get_coords(W2, H2, torch.device("cpu"))
+torch.manual_seed(seed)
+eps_expected = (0.5 / H2) * torch.rand(1) / 2.0            # training.py:198-200
+torch.manual_seed(seed)
+with torch.no_grad():
+    rgb2 = tr.predict_lip_image(0, coords2, audio[1:2], None, {"index": torch.tensor([idx2])}, None, None, None)
+ens = {"grid_ens4_kaiming_12x256_i9/audio": audio[1:2].numpy(), "grid_ens4_kaiming_12x256_i9/index": np.int64(idx2),
+       "grid_ens4_kaiming_12x256_i9/eps": eps_expected.numpy(), "grid_ens4_kaiming_12x256_i9/rng_seed": np.int64(seed),
+       "grid_ens4_kaiming_12x256_i9/rgb": rgb2.reshape(H2, W2, 3).numpy()}
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden_grid.npz"),
                     **{"grid_kaiming_40x256_i7/audio": audio[2:3].numpy(), "grid_kaiming_40x256_i7/index": np.int64(idx),
                        "grid_kaiming_40x256_i7/coords": coords.numpy(),
-                       "grid_kaiming_40x256_i7/rgb": out[:, :3].reshape(H, W, 3).numpy()})
+                       "grid_kaiming_40x256_i7/rgb": out[:, :3].reshape(H, W, 3).numpy()}, **ens)
 print("wrote reference_golden_grid.npz", out.shape, float(out.abs().max()))

@@ -669,3 +669,18 @@ def test_wide_grid_vs_golden(S, golden):
         err = maxabs(rgb[0].cpu(), g["rgb"])
         print("wide grid %s maxabs %.3e" % (precision, err))
         assert err < tol
+
+
+def test_wide_grid_ensemble4_vs_golden(S, golden):
+    """the real Trainer.predict_lip_image at W = 256 (RNG-aligned eps): tap coordinates = fused-linspace grid + shifts."""
+    g = golden["grid_ens4_kaiming_12x256_i9"]
+    torch.manual_seed(int(g["rng_seed"]))
+    eps = float(((0.5 / 12) * torch.rand(1) / 2.0).item())
+    assert eps == float(g["eps"][0])
+    for precision, tol in (("fp32", 1.5e-5), ("bf16x3", 3e-4), ("fp16f8", PARITY_TOL)):
+        r = S.LipRenderer(packed(S, "kaiming"), precision)
+        rgb = r.render_frames(torch.from_numpy(g["audio"]).to(dev()), torch.tensor([int(g["index"])]), 12, 256, mode="ensemble4",
+                              eps_shift=eps)
+        err = maxabs(rgb[0].cpu(), g["rgb"])
+        print("wide grid ens4 %s maxabs %.3e" % (precision, err))
+        assert err < tol

@@ -149,3 +149,11 @@ def test_wide_grid_case_pins_the_fused_linspace(golden):
     with torch.no_grad():
         rgb = O.render_plain(sd, torch.from_numpy(g["audio"]), int(g["index"]), 40, 256)
     assert np.abs(rgb.numpy() - g["rgb"]).max() < 2e-5
+
+
+def test_wide_ensemble4_case_oracle(golden):
+    g = golden["grid_ens4_kaiming_12x256_i9"]
+    sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming"))
+    with torch.no_grad():
+        rgb = O.render_ensemble4(sd, torch.from_numpy(g["audio"]), int(g["index"]), 12, 256, float(g["eps"][0]))
+    assert np.abs(rgb.numpy() - g["rgb"]).max() < 2e-5
