@@ -1,7 +1,7 @@
 // speech2lip_b200 — shared definitions: packed-blob layout, PTX helpers, launch bookkeeping.
 //
 // Data layout in HBM (one blob per model, written by s2l_pack_weights, read-only afterwards,
-// ~6 MB -> L2-resident during a render):
+// ~9 MB -> L2-resident during a render):
 //   AUDIO   fp32  AudioNet parameters in their PyTorch layouts (tf_nerf.py:91-109)
 //   CONST   fp32  per-frame-constant mat-vec weights (fc_audio/fc_time + *_skip), bias vectors,
 //                 time div_term, folded input weights fold0 = W0*Wuv, fold5 = W5a*Wuv_skip
