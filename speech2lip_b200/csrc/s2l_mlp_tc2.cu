@@ -17,6 +17,7 @@
 //     tcgen05.commit multicasts accumulator-ready / stage-free / PE-free events to both CTAs.
 //   * every CTA of the grid runs the same number of tile iterations (iterations past the end compute on zero rows and
 //     store nothing) so the pair stays in lock step.
+#include <cstdlib>
 #include <type_traits>
 #include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "s2l_tc_common.cuh"
@@ -507,6 +508,10 @@ static int launch_tc2_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) 
 }
 
 int launch_mlp_tc2(const TcArgs& a, long long n_tiles, int npass, cudaStream_t st) {
+  if (getenv("S2L_TEST_FAIL_PAIR")) {     // test hook: behave like a device / driver that cannot run the pair schedule
+    set_error("mlp_tc2: pair schedule disabled by S2L_TEST_FAIL_PAIR");
+    return 7;
+  }
   if (a.src.uv_dims == 2)
     return npass == 3 ? launch_tc2_impl<3, 2>(a, n_tiles, st) : npass == 2 ? launch_tc2_impl<2, 2>(a, n_tiles, st) : launch_tc2_impl<1, 2>(a, n_tiles, st);
   return npass == 3 ? launch_tc2_impl<3, 3>(a, n_tiles, st) : npass == 2 ? launch_tc2_impl<2, 3>(a, n_tiles, st) : launch_tc2_impl<1, 3>(a, n_tiles, st);

@@ -684,3 +684,36 @@ def test_wide_grid_ensemble4_vs_golden(S, golden):
         err = maxabs(rgb[0].cpu(), g["rgb"])
         print("wide grid ens4 %s maxabs %.3e" % (precision, err))
         assert err < tol
+
+
+def test_pair_schedule_unavailable_falls_back_or_fails_loudly(S):
+    """a device / driver that cannot run the CTA-pair schedule (simulated with S2L_TEST_FAIL_PAIR): an automatically
+    selected pair launch falls back to the single-CTA schedule (same arithmetic, bit-identical), a FORCED one raises."""
+    import subprocess, sys, tempfile
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import speech2lip_b200 as s2l
+from speech2lip_b200 import synth
+dev = torch.device("cuda:0")
+sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
+w = s2l.PackedWeights(sd)
+a = torch.from_numpy(synth.make_audio(4, seed=5)).to(dev)
+try:
+    out = s2l.LipRenderer(w, "bf16x3").render_frames(a, torch.arange(4), 200, 200)      # 4 x 313 tiles >= 8 per SM -> pair schedule
+    torch.save(out.cpu(), sys.argv[1])
+    print("OK")
+except RuntimeError as e:
+    print("RAISED", str(e)[:80])
+""" % ROOT
+    d = tempfile.mkdtemp()
+    runs = {}
+    for name, env in (("pair", {}), ("fallback", {"S2L_TEST_FAIL_PAIR": "1"}), ("forced", {"S2L_TEST_FAIL_PAIR": "1", "S2L_TC_IMPL": "2"})):
+        e = dict(os.environ, **env)
+        if name != "forced":
+            e.pop("S2L_TC_IMPL", None)
+        r = subprocess.run([sys.executable, "-c", code, os.path.join(d, name + ".pt")], env=e, capture_output=True, text=True, timeout=600)
+        runs[name] = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-200:]
+    assert runs["pair"] == "OK" and runs["fallback"] == "OK", runs
+    assert runs["forced"].startswith("RAISED"), runs
+    assert torch.equal(torch.load(os.path.join(d, "pair.pt")), torch.load(os.path.join(d, "fallback.pt")))
