@@ -167,3 +167,14 @@ def test_bench_constants_and_traffic_helper_cpu():
     one = b.ncu_traffic(t["frames_per_launch"], t["points_per_launch"])
     assert one == t["dram_bytes_read"] + t["dram_bytes_write"]
     assert abs(b.ncu_traffic(8, t["points_per_launch"]) - 8 * one) < 1e-6 * one
+
+
+def test_drop_in_helper_entry_points_report_errors():
+    """s2l_latent_bias_fwd / s2l_rows_differ validate their arguments before touching the device."""
+    lib = _cabi.lib()
+    assert lib.s2l_latent_bias_fwd(None, None, 64, None, None, 1, None) == 1 and b"null" in lib.s2l_last_error()
+    assert lib.s2l_latent_bias_fwd(C.c_void_p(16), C.c_void_p(16), 64, None, C.c_void_p(16), -1, None) == 2
+    assert lib.s2l_latent_bias_fwd(C.c_void_p(16), C.c_void_p(16), 64, None, C.c_void_p(16), 0, None) == 0     # empty batch: no launch
+    assert lib.s2l_rows_differ(None, 4, 8, 0, 8, None, None) == 1 and b"null" in lib.s2l_last_error()
+    assert lib.s2l_rows_differ(C.c_void_p(16), 4, 8, 4, 8, C.c_void_p(16), None) == 2 and b"shape" in lib.s2l_last_error()
+    assert lib.s2l_tc_schedule(0) in (1, 2, 3)
