@@ -1,6 +1,6 @@
 """Soak test of a tensor-core schedule (S2L_TC_IMPL=1|2|3 in the environment): many launches of random, ragged geometries
 (different tile counts, dead tail iterations, both precisions, plain / ensemble4) compared with the exact fp32 path, plus a
-long run of chip-filling launches compared with the first one bit for bit.  usage: stress_schedules.py [n_random] [n_big]"""
+long run of chip-filling launches compared with the first one bit for bit.  usage: stress_schedules.py [n_random] [n_big] [weight_seed]"""
 import os, random, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,8 +10,9 @@ from speech2lip_b200 import synth
 
 n_random = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 n_big = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+wseed = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # seed of the synthetic (kaiming) weights
 dev = torch.device("cuda:0")
-sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(0, "kaiming").items()}
+sd = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_state_dict(wseed, "kaiming").items()}
 w = s2l.PackedWeights(sd)
 exact = s2l.LipRenderer(w, "fp32")
 rnd = random.Random(0)
@@ -30,7 +31,7 @@ for it in range(n_random):
     err = (got - want).abs().max().item()
     worst[prec] = max(worst[prec], err)
     assert err < (3e-4 if prec == "bf16x3" else 1e-3), (it, F, H, W, mode, prec, err)
-print("random geometries: %d launches ok in %.1f s, worst max-abs vs fp32 path %s" % (n_random, time.time() - t0, worst))
+print("weights seed %d, random geometries: %d launches ok in %.1f s, worst max-abs vs fp32 path %s" % (wseed, n_random, time.time() - t0, worst))
 F, H, W = 64, 256, 256
 audio = torch.from_numpy(synth.make_audio(F, seed=1)).to(dev)
 idx = torch.arange(F)
