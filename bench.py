@@ -225,29 +225,21 @@ def run_gpu_arm(a):
                          pts_mode={"volumetric": _cabi.PTS_RAYS, "plain": _cabi.PTS_GRID, "ensemble4": _cabi.PTS_GRID_ENS4}[a.mode],
                          uv_dims=uvd, out_ch=och, z_per_ray=0, rays_per_frame_shared=1, pts_per_frame=0, eps_shift=0.001)
     P = points_per_frame(a)
-    bias_d = torch.empty(F, 4, 256, device=dev)
-    raw_d = rgb_d if a.mode == "plain" else torch.empty(F * P * och, device=dev)
     ro_d = torch.empty(H, W, 3, device=dev)
     rd_d = torch.empty(H, W, 3, device=dev)
     prec = _cabi.PRECISIONS[a.precision]
     st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = R._ptr
+    scratch_d = torch.empty(lib.s2l_render_scratch_bytes(C.byref(geom), prec, 0), dtype=torch.uint8, device=dev)
 
-    def step_device(ev=None):
-        """the decomposed whole-path call (identical kernels to s2l_render_frames) with events around the fused MLP"""
+    def step_device():
+        """the whole-path C-ABI call on device-resident inputs: ray generation, then s2l_render_frames = AudioNet + per-frame
+        biases -> fused MLP with the per-pixel reduction in its epilogue -> fp32 re-evaluation of the listed rays.  The
+        fused-MLP launches are bracketed by CUDA events inside the library (s2l_profile_enable) for the roofline."""
         if vol:
             _cabi.check(lib.s2l_get_rays(p(c2w_d), H, W, 1200.0, p(ro_d), p(rd_d), st()), "get_rays")
-        _cabi.check(lib.s2l_audio_encode_fwd(p(w.blob), p(audio_d), 0, p(index_d), None, p(bias_d), F, uvd, och, st()), "audio")
-        if ev:
-            ev[0].record()
-        _cabi.check(lib.s2l_mlp_fwd(p(w.blob), C.byref(geom), p(bias_d), None, p(ro_d) if vol else None, p(rd_d) if vol else None,
-                                    p(z_d), p(raw_d), prec, st()), "mlp")
-        if ev:
-            ev[1].record()
-        if vol:
-            _cabi.check(lib.s2l_composite_fwd(p(raw_d), p(z_d), 0, p(rd_d), H * W * F, H * W, a.samples, p(rgb_d), None, None, st()), "composite")
-        elif a.mode == "ensemble4":
-            _cabi.check(lib.s2l_ensemble4_blend(p(raw_d), C.byref(geom), p(rgb_d), st()), "blend")
+        _cabi.check(lib.s2l_render_frames(p(w.blob), C.byref(geom), p(audio_d), p(index_d), p(ro_d) if vol else None,
+                                          p(rd_d) if vol else None, p(z_d), p(rgb_d), None, None, p(scratch_d), prec, st()), "render")
 
     def step_e2e():
         """public API on HOST buffers: H2D (windows, indices, pose) -> render -> D2H (frames), all on the current stream"""
@@ -270,17 +262,19 @@ def run_gpu_arm(a):
     def timed(fn, steps, with_kernel_events):
         tot = 0.0
         ker = 0.0
+        if with_kernel_events:
+            lib.s2l_profile_enable(1)
         for _ in range(steps):
             flush.fill_(1)                                    # evict L2 between timed iterations (untimed)
             e0, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] if with_kernel_events else None
             e0.record()
-            fn(ev) if with_kernel_events else fn()
+            fn()
             e3.record()
             e3.synchronize()
             tot += e0.elapsed_time(e3)
-            if ev:
-                ker += ev[0].elapsed_time(ev[1])
+        if with_kernel_events:
+            ker = float(lib.s2l_profile_mlp_ms(None))
+            lib.s2l_profile_enable(0)
         return tot, ker
 
     # ---- warm-up (untimed), then the timed region bracketed by barrier + synchronize
@@ -424,7 +418,7 @@ def run_gpu_arm(a):
                     "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": e2e_ms / a.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor" if tensor_bound else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(F, P), "kernel": ({1: "mlp_tc_kernel", 2: "mlp_tc2_kernel (CTA pairs)", 3: "mlp_tc_kernel (2-CTA multicast weights)"}[tc_sched] if tensor_bound else "mlp_fp32_kernel"),
+                         "traffic": ncu_traffic(F, P, a.precision), "kernel": ({1: "mlp_tc_kernel", 2: "mlp_tc2_kernel (CTA pairs)", 3: "mlp_tc_kernel (2-CTA multicast weights)"}[tc_sched] if tensor_bound else "mlp_fp32_kernel"),
                          "kernel_ms_per_launch": ker_ms / a.steps, "flop_per_point_algorithmic": FLOP_PER_POINT[a.mode],
                          "mma_multiplier": {"bf16x3": 3, "fp16f8": 2}.get(a.precision, 1), "peak_source": peak_src,
                          "frac_of_burst_peak": ach / peaks["bf16_tflops"] if tensor_bound and peaks.get("bf16_tflops") else None,
@@ -454,15 +448,19 @@ def run_gpu_arm(a):
         dist.destroy_process_group()
 
 
-def ncu_traffic(frames, pts_per_frame):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel from the committed ncu capture
-    (profiles/ncu_traffic.json), scaled from the captured launch to this launch's point count; None if absent."""
+def ncu_traffic(frames, pts_per_frame, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused MLP kernel from the committed `ncu --set full`
+    capture of THIS launch geometry (profiles/ncu_traffic.json: one record per captured geometry; no scaling between
+    geometries — L2 residency changes with the launch size); None when that geometry was never captured."""
     try:
         import json as _j
-        t = _j.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
-        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (float(frames) * pts_per_frame / t["points_per_launch"])
+        recs = _j.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        for t in recs if isinstance(recs, list) else [recs]:
+            if t["points_per_launch"] == frames * pts_per_frame and t.get("precision") == precision and t.get("fused_epilogue"):
+                return t["dram_bytes_read"] + t["dram_bytes_write"]
     except Exception:
-        return None
+        pass
+    return None
 
 
 def main():

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define S2L_ABI_VERSION 1
+#define S2L_ABI_VERSION 2
 
 /* Number of parameter tensors s2l_pack_weights() reads, in this fixed order
  * (reference state_dict names, tf_nerf.py:85-172):                                  */
@@ -83,6 +83,16 @@ typedef struct S2LGeom {
   const float* eps_per_frame; /* GRID_ENS4, optional DEVICE array [F]: one draw per frame (the sync-window
                                  render calls predict_lip_image once per frame, training.py:504-525);
                                  NULL -> eps_shift is used for every frame                             */
+  /* ---- ABI v2: volumetric (RAYS) rendering options of s2l_render_frames; all-zero = v1 behaviour + the default fix_thr */
+  int32_t sample_chunks;   /* 0/1: every sample of every ray in one launch.  C > 1 (C | S, S/C in {4,8,...,128}): C front-to-back
+                              launches of S/C samples with EARLY RAY TERMINATION — after each chunk rays whose transmittance
+                              fell below term_thr are finished (what is left would change the pixel by < term_thr) and only the
+                              survivors (compacted per frame on the device) enter the next chunk                               */
+  float   term_thr;        /* early-ray-termination threshold on the transmittance (e.g. 1e-4); <= 0 with C > 1: chunked, never terminates */
+  float   fix_thr;         /* tensor-core precisions: rays whose LAST sample's density is within fix_thr of zero are re-evaluated
+                              in exact fp32 (density2outputs gives the last sample delta = 1e10, rendering.py:44, so alpha_last is a
+                              step function of sign(sigma_last) and a rounding error there flips the pixel).  0 -> default 2e-3
+                              (3x the worst tensor-core density error measured), < 0 -> off                                    */
 } S2LGeom;
 
 /* Thread-local description of the last error (never NULL). */
@@ -170,10 +180,18 @@ int32_t s2l_get_rays(const float* c2w, int32_t height, int32_t width, float foca
                      float* rays_o, float* rays_d, void* stream);
 
 /* Whole-path call on device buffers: AudioNet -> MLP -> per-pixel reduction for F frames.
- *   rgb [F,H,W,3] out; scratch must hold s2l_render_scratch_bytes(geom) bytes.
+ *   rgb [F,H,W,3] out; scratch must hold s2l_render_scratch_bytes(geom, precision, want_aux) bytes
+ *   (want_aux = weights or depth requested).
  * Replaces the loop body of inference.py:144-159 (GRID), training.py:158-251 (GRID_ENS4) or the
- * assembled volumetric path (RAYS). */
-size_t  s2l_render_scratch_bytes(const S2LGeom* geom);
+ * assembled volumetric path (RAYS).
+ * With a tensor-core precision the per-pixel reduction (4-tap blend, alpha compositing) runs inside the MLP kernel's
+ * output-layer epilogue and the raw [P,out_ch] tensor never exists in memory; the unfused composition (MLP -> raw ->
+ * s2l_composite_fwd / s2l_ensemble4_blend) serves S2L_PREC_FP32, weights/depth outputs and sample counts S with
+ * S % 4 != 0 or 128 % S != 0. */
+size_t  s2l_render_scratch_bytes(const S2LGeom* geom, int32_t precision, int32_t want_aux);
+/* Byte offset inside `scratch` of the int32 counters a RAYS render leaves behind: counts[k*F + f], k = 1..C-1 = rays of
+ * frame f still alive when sample chunk k started, k = C (C = max(sample_chunks,1)) = rays of frame f re-evaluated in fp32. */
+size_t  s2l_render_counts_offset(const S2LGeom* geom);
 int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, const float* audio, const int64_t* frame_idx,
                           const float* rays_o, const float* rays_d, const float* z_vals,
                           float* rgb, float* weights, float* depth, void* scratch, int32_t precision,
@@ -200,6 +218,15 @@ int32_t s2l_audio_windows(const float* logits, int64_t n_steps, float* windows, 
  * x*255 in fp32, round-half-even, saturate to [0,255], channel swap): rgb [N_pixels,3] fp32 -> bgr [N_pixels,3] u8.
  * Cuts the device->host bytes of a finished frame 4x. */
 int32_t s2l_frames_to_bgr8(const float* rgb, int64_t n_pixels, uint8_t* bgr, void* stream);
+
+/* sizeof(S2LGeom) as this library was compiled (bindings check their struct definition against it). */
+int32_t s2l_sizeof_geom(void);
+
+/* Measurement aid (bench.py "roofline"): while enabled, every launch of the fused tensor-core MLP kernel is bracketed by
+ * CUDA events on the stream it is launched on.  s2l_profile_mlp_ms synchronises on the recorded events, returns the summed
+ * kernel time in ms since the last call (and the number of launches in *n_launches, may be NULL) and clears the record. */
+void    s2l_profile_enable(int32_t on);
+double  s2l_profile_mlp_ms(int32_t* n_launches);
 
 /* Number of kernels of this library launched by this thread since the last reset (bench "gpu_launches"). */
 int64_t s2l_launch_count(int32_t reset);

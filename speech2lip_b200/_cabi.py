@@ -31,7 +31,9 @@ class S2LGeom(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_samples", C.c_int32),
                 ("pts_mode", C.c_int32), ("uv_dims", C.c_int32), ("out_ch", C.c_int32), ("z_per_ray", C.c_int32),
                 ("rays_per_frame_shared", C.c_int32), ("pts_per_frame", C.c_int64), ("eps_shift", C.c_float),
-                ("eps_per_frame", C.c_void_p)]
+                ("eps_per_frame", C.c_void_p),
+                # ABI v2: volumetric options (sample chunks + early ray termination, fp32 re-evaluation threshold)
+                ("sample_chunks", C.c_int32), ("term_thr", C.c_float), ("fix_thr", C.c_float)]
 
 
 SYMBOLS = {
@@ -56,12 +58,16 @@ SYMBOLS = {
     "s2l_composite_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "s2l_get_rays": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "s2l_render_scratch_bytes": (C.c_size_t, [C.POINTER(S2LGeom)]),
+    "s2l_render_scratch_bytes": (C.c_size_t, [C.POINTER(S2LGeom), C.c_int32, C.c_int32]),
+    "s2l_render_counts_offset": (C.c_size_t, [C.POINTER(S2LGeom)]),
     "s2l_render_frames": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "s2l_post_fusion_compose": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p] * 3),
     "s2l_audio_windows": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "s2l_frames_to_bgr8": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "s2l_sizeof_geom": (C.c_int32, []),
+    "s2l_profile_enable": (None, [C.c_int32]),
+    "s2l_profile_mlp_ms": (C.c_double, [C.POINTER(C.c_int32)]),
     "s2l_launch_count": (C.c_int64, [C.c_int32]),
     "s2l_tc_schedule": (C.c_int32, [C.c_int64]),
 }
@@ -81,6 +87,9 @@ def lib():
             fn = getattr(l, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
+        if l.s2l_sizeof_geom() != C.sizeof(S2LGeom):
+            raise RuntimeError("speech2lip_b200: S2LGeom is %d bytes in the binding, %d in %s (stale build?)"
+                               % (C.sizeof(S2LGeom), l.s2l_sizeof_geom(), LIB_PATH))
         _lib = l
     return _lib
 

@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <utility>
+#include <vector>
 #include "s2l_common.cuh"
 #include "s2l_points.cuh"
 
@@ -27,15 +29,37 @@ bool check_launch(const char* what) {
   return true;
 }
 
+// ---- bench.py's live kernel timing: CUDA events around every fused-MLP launch, on the launching stream
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static size_t g_prof_used = 0;
+void profile_mark(cudaStream_t st, int which) {
+  if (!g_prof_on) return;
+  if (which == 0) {
+    if (g_prof_used == g_prof_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      g_prof_pool.emplace_back(a, b);
+    }
+    cudaEventRecord(g_prof_pool[g_prof_used].first, st);
+  } else if (g_prof_used < g_prof_pool.size()) {
+    cudaEventRecord(g_prof_pool[g_prof_used].second, st);
+    ++g_prof_used;
+  }
+}
+
 int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out,
-                    int out_ch, cudaStream_t st);
+                    int out_ch, cudaStream_t st, const float4* fix_carry = nullptr, float* fix_rgb = nullptr,
+                    float* patch_raw = nullptr);
+int launch_tile_scan(const int* count, int F, int Sc, int* ts128, int* ts64, cudaStream_t st);
+int launch_flag_last(const float* raw, int F, int R, int S, float thr, int* count, int* rays, cudaStream_t st);
 int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, long long time_idx, int has_time,
                          float* out, float* save, int uv_dims, int out_ch, cudaStream_t st);
 int launch_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts, long long n_rows, float* dsave,
                         int out_ch, cudaStream_t st);
 int launch_embed(const float* x, long long n_rows, int row_stride, int uv_dims, float* pe, cudaStream_t st);
 int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
-                  int npass, cudaStream_t st);
+                  int npass, cudaStream_t st, const TcEpi* epi = nullptr);
 
 static long long points_per_frame(const S2LGeom& g) {
   switch (g.pts_mode) {
@@ -77,6 +101,9 @@ static PointSrc make_src(const S2LGeom& g, const float* pts, const float* ro, co
   s.eps = g.eps_shift;
   s.eps_pf = (g.pts_mode == S2L_PTS_GRID_ENS4) ? g.eps_per_frame : nullptr;
   s.P = points_per_frame(g);
+  s.R = g.height * g.width;
+  s.s0 = 0;
+  s.Sc = s.S;
   s.pts = pts;
   s.rays_o = ro;
   s.rays_d = rd;
@@ -94,6 +121,23 @@ extern "C" int64_t s2l_launch_count(int32_t reset) {
   const long long v = g_launches;
   if (reset) g_launches = 0;
   return v;
+}
+
+extern "C" int32_t s2l_sizeof_geom(void) { return (int32_t)sizeof(S2LGeom); }
+extern "C" void s2l_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  if (on) g_prof_used = 0;
+}
+extern "C" double s2l_profile_mlp_ms(int32_t* n_launches) {
+  double ms = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float t = 0.f;
+    cudaEventSynchronize(g_prof_pool[i].second);
+    if (cudaEventElapsedTime(&t, g_prof_pool[i].first, g_prof_pool[i].second) == cudaSuccess) ms += t;
+  }
+  if (n_launches) *n_launches = (int32_t)g_prof_used;
+  g_prof_used = 0;
+  return ms;
 }
 
 extern "C" int32_t s2l_mlp_fwd(const void* blob, const S2LGeom* geom, const float* frame_bias, const float* pts,
@@ -145,13 +189,60 @@ extern "C" int32_t s2l_embed_fwd(const float* x, int64_t n_rows, int32_t row_str
   return launch_embed(x, n_rows, row_stride, uv_dims, pe, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t s2l_render_scratch_bytes(const S2LGeom* g) {
+// ---- whole-path orchestration ------------------------------------------------------------------------------------
+static int npass_of(int precision) {
+  return precision == S2L_PREC_BF16X3 ? 3 : precision == S2L_PREC_BF16X1 ? 1 : precision == S2L_PREC_FP16F8 ? 2 : 0;
+}
+
+// What a s2l_render_frames call does and where its scratch sections live.
+struct RenderPlan {
+  bool tc, fused, fix;
+  int chunks, Sc;
+  float fix_thr, term_thr;
+  size_t off_bias, off_carry, off_list[2], off_counts, off_ts128, off_ts64, off_raw, total;
+};
+static RenderPlan make_plan(const S2LGeom& g, int precision, bool want_aux) {
+  RenderPlan p{};
+  const long long P = points_per_frame(g);
+  const size_t F = (size_t)(g.n_frames > 0 ? g.n_frames : 0);
+  const size_t R = (size_t)g.height * (size_t)g.width;
+  p.tc = npass_of(precision) != 0;
+  p.chunks = 1;
+  p.Sc = g.n_samples;
+  const bool rays = g.pts_mode == S2L_PTS_RAYS;
+  auto chunk_ok = [](int sc) { return sc >= 4 && sc <= 128 && (sc & 3) == 0 && 128 % sc == 0; };
+  if (rays && p.tc && !want_aux && g.sample_chunks > 1 && g.n_samples % g.sample_chunks == 0 && chunk_ok(g.n_samples / g.sample_chunks)) {
+    p.chunks = g.sample_chunks;
+    p.Sc = g.n_samples / g.sample_chunks;
+  }
+  p.fused = p.tc && ((rays && !want_aux && g.out_ch == 4 && chunk_ok(p.Sc)) || (g.pts_mode == S2L_PTS_GRID_ENS4 && g.out_ch == 3));
+  p.fix_thr = g.fix_thr == 0.f ? 2e-3f : g.fix_thr;
+  p.fix = rays && p.tc && precision != S2L_PREC_BF16X1 && p.fix_thr > 0.f;      // bf16x1 is a preview mode: no parity claim to protect
+  p.term_thr = g.term_thr;
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t o = 0;
+  p.off_bias = o;   o = al(o + F * 4 * 256 * sizeof(float));
+  const bool lists = rays && p.tc && (p.fix || p.chunks > 1);
+  p.off_carry = o;  if (lists && p.fused) o = al(o + F * R * sizeof(float4));
+  p.off_list[0] = o; if (lists) o = al(o + F * R * sizeof(int));
+  p.off_list[1] = o; if (lists && p.chunks > 1) o = al(o + F * R * sizeof(int));
+  p.off_counts = o; if (lists) o = al(o + (size_t)(p.chunks + 1) * F * sizeof(int));
+  p.off_ts128 = o;  if (lists) o = al(o + (F + 1) * sizeof(int));
+  p.off_ts64 = o;   if (lists) o = al(o + (F + 1) * sizeof(int));
+  p.off_raw = o;
+  const bool direct = (g.pts_mode == S2L_PTS_GRID && g.out_ch == 3);
+  if (!p.fused && !direct && P > 0) o = al(o + F * (size_t)P * g.out_ch * sizeof(float));
+  p.total = o + 256;
+  return p;
+}
+
+extern "C" size_t s2l_render_scratch_bytes(const S2LGeom* g, int32_t precision, int32_t want_aux) {
+  if (!g || points_per_frame(*g) < 0) return 0;
+  return make_plan(*g, precision, want_aux != 0).total;
+}
+extern "C" size_t s2l_render_counts_offset(const S2LGeom* g) {
   if (!g) return 0;
-  const long long P = points_per_frame(*g);
-  if (P < 0) return 0;
-  size_t bias = (size_t)g->n_frames * 4 * 256 * sizeof(float);
-  size_t raw = (g->pts_mode == S2L_PTS_GRID && g->out_ch == 3) ? 0 : (size_t)g->n_frames * (size_t)P * g->out_ch * sizeof(float);
-  return ((bias + 255) & ~size_t(255)) + raw + 256;
+  return make_plan(*g, S2L_PREC_FP16F8, false).off_counts;
 }
 
 extern "C" int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, const float* audio, const int64_t* frame_idx,
@@ -162,20 +253,103 @@ extern "C" int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, cons
   if (!blob || !audio || !rgb || !scratch) { set_error("s2l_render_frames: null blob/audio/rgb/scratch"); return 1; }
   if (geom->pts_mode == S2L_PTS_EXPLICIT) { set_error("s2l_render_frames: EXPLICIT points are served by s2l_mlp_fwd"); return 2; }
   if (geom->pts_mode == S2L_PTS_RAYS && geom->out_ch != 4) { set_error("s2l_render_frames: ray mode needs the out_ch=4 model"); return 2; }
-  float* bias = reinterpret_cast<float*>(scratch);
-  const size_t bias_bytes = (((size_t)geom->n_frames * 4 * 256 * sizeof(float)) + 255) & ~size_t(255);
-  float* raw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + bias_bytes);
-  int rc = s2l_audio_encode_fwd(blob, audio, 0, frame_idx, nullptr, bias, geom->n_frames, geom->uv_dims, geom->out_ch, stream);
-  if (rc) return rc;
-  const bool direct = (geom->pts_mode == S2L_PTS_GRID && geom->out_ch == 3);
-  rc = s2l_mlp_fwd(blob, geom, bias, nullptr, rays_o, rays_d, z_vals, direct ? rgb : raw, precision, stream);
-  if (rc) return rc;
-  if (geom->pts_mode == S2L_PTS_GRID) {
-    if (!direct) { set_error("s2l_render_frames: GRID mode needs the out_ch=3 model"); return 2; }
-    return 0;
+  if (geom->pts_mode == S2L_PTS_GRID && geom->out_ch != 3) { set_error("s2l_render_frames: GRID mode needs the out_ch=3 model"); return 2; }
+  if (geom->pts_mode == S2L_PTS_RAYS && (!rays_o || !rays_d || !z_vals)) { set_error("s2l_render_frames: RAYS mode needs rays_o, rays_d, z_vals"); return 1; }
+  if (precision < S2L_PREC_FP32 || precision > S2L_PREC_FP16F8) { set_error("s2l_render_frames: unknown precision %d", precision); return 2; }
+  const bool want_aux = weights || depth;
+  const RenderPlan pl = make_plan(*geom, precision, want_aux);
+  if (geom->pts_mode == S2L_PTS_RAYS && geom->sample_chunks > 1 && pl.chunks == 1) {
+    set_error("s2l_render_frames: sample_chunks=%d needs a tensor-core precision, no weights/depth outputs and "
+              "n_samples/sample_chunks in {4,8,...,128} (n_samples=%d)", geom->sample_chunks, geom->n_samples);
+    return 2;
   }
-  if (geom->pts_mode == S2L_PTS_GRID_ENS4) return s2l_ensemble4_blend(raw, geom, rgb, stream);
-  const long long R = (long long)geom->height * geom->width;
-  return s2l_composite_fwd(raw, z_vals, geom->z_per_ray, rays_d, R * geom->n_frames,
-                           geom->rays_per_frame_shared ? R : 0, geom->n_samples, rgb, weights, depth, stream);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
+  float* bias = reinterpret_cast<float*>(sc + pl.off_bias);
+  float* raw = reinterpret_cast<float*>(sc + pl.off_raw);
+  float4* carry = reinterpret_cast<float4*>(sc + pl.off_carry);
+  int* lists[2] = {reinterpret_cast<int*>(sc + pl.off_list[0]), reinterpret_cast<int*>(sc + pl.off_list[1])};
+  int* counts = reinterpret_cast<int*>(sc + pl.off_counts);
+  int* ts128 = reinterpret_cast<int*>(sc + pl.off_ts128);
+  int* ts64 = reinterpret_cast<int*>(sc + pl.off_ts64);
+  const int F = geom->n_frames;
+  const int R = geom->height * geom->width;
+  const int np = npass_of(precision);
+  int rc = s2l_audio_encode_fwd(blob, audio, 0, frame_idx, nullptr, bias, F, geom->uv_dims, geom->out_ch, stream);
+  if (rc) return rc;
+
+  if (geom->pts_mode == S2L_PTS_GRID)
+    return s2l_mlp_fwd(blob, geom, bias, nullptr, nullptr, nullptr, nullptr, rgb, precision, stream);
+
+  if (geom->pts_mode == S2L_PTS_GRID_ENS4) {
+    if (pl.fused) {
+      const PointSrc src = make_src(*geom, nullptr, nullptr, nullptr, nullptr);
+      TcEpi epi{};
+      epi.mode = EPI_ENS4;
+      epi.rgb = rgb;
+      return launch_mlp_tc(blob, src, F, bias, nullptr, geom->out_ch, np, st, &epi);
+    }
+    rc = s2l_mlp_fwd(blob, geom, bias, nullptr, nullptr, nullptr, nullptr, raw, precision, stream);
+    if (rc) return rc;
+    return s2l_ensemble4_blend(raw, geom, rgb, stream);
+  }
+
+  // ---- RAYS
+  const bool lists_used = pl.tc && (pl.fix || pl.chunks > 1);
+  if (lists_used && cudaMemsetAsync(counts, 0, (size_t)(pl.chunks + 1) * F * sizeof(int), st) != cudaSuccess) {
+    set_error("s2l_render_frames: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 5;
+  }
+  // list of rays the fp32 kernel re-evaluates at their last sample
+  PointSrc fixsrc = make_src(*geom, nullptr, rays_o, rays_d, z_vals);
+  fixsrc.s0 = geom->n_samples - 1;
+  fixsrc.Sc = 1;
+  fixsrc.P = R;
+  fixsrc.list_count = counts + (size_t)pl.chunks * F;
+  fixsrc.tile_start = ts64;
+
+  if (!pl.fused) {
+    rc = s2l_mlp_fwd(blob, geom, bias, nullptr, rays_o, rays_d, z_vals, raw, precision, stream);
+    if (rc) return rc;
+    if (pl.fix) {
+      int* fcount = counts + (size_t)pl.chunks * F;
+      if ((rc = launch_flag_last(raw, F, R, geom->n_samples, pl.fix_thr, fcount, lists[0], st))) return rc;
+      if ((rc = launch_tile_scan(fcount, F, 1, ts128, ts64, st))) return rc;
+      fixsrc.list_rays = lists[0];
+      if ((rc = launch_mlp_fp32(blob, fixsrc, F, bias, nullptr, 4, st, nullptr, nullptr, raw))) return rc;
+    }
+    return s2l_composite_fwd(raw, z_vals, geom->z_per_ray, rays_d, (long long)R * F, geom->rays_per_frame_shared ? R : 0,
+                             geom->n_samples, rgb, weights, depth, stream);
+  }
+
+  // fused: C launches of Sc samples; launch c reads list c (c >= 1) and appends to list c + 1 (survivors) or, on the
+  // last chunk, to the fp32 re-evaluation list
+  for (int c = 0; c < pl.chunks; ++c) {
+    PointSrc src = make_src(*geom, nullptr, rays_o, rays_d, z_vals);
+    src.s0 = c * pl.Sc;
+    src.Sc = pl.Sc;
+    src.P = (long long)R * pl.Sc;
+    if (c > 0) {
+      src.list_count = counts + (size_t)c * F;
+      src.list_rays = lists[(c - 1) & 1];
+      src.tile_start = ts128;
+      if ((rc = launch_tile_scan(src.list_count, F, pl.Sc, ts128, ts64, st))) return rc;
+    }
+    const bool last = (c == pl.chunks - 1);
+    TcEpi epi{};
+    epi.mode = EPI_COMPOSITE;
+    epi.rgb = rgb;
+    epi.carry = carry;
+    epi.next_count = counts + (size_t)(c + 1) * F;
+    epi.next_rays = lists[c & 1];
+    epi.term_thr = pl.term_thr;
+    epi.fix_thr = (last && pl.fix) ? pl.fix_thr : 0.f;
+    if ((rc = launch_mlp_tc(blob, src, F, bias, nullptr, 4, np, st, &epi))) return rc;
+  }
+  if (pl.fix) {
+    if ((rc = launch_tile_scan(fixsrc.list_count, F, 1, ts128, ts64, st))) return rc;
+    fixsrc.list_rays = lists[(pl.chunks - 1) & 1];
+    if ((rc = launch_mlp_fp32(blob, fixsrc, F, bias, nullptr, 4, st, carry, rgb, nullptr))) return rc;
+  }
+  return 0;
 }

@@ -199,6 +199,15 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   const float step = __fdiv_rn(1.0f, (float)(n - 1));
   return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
 }
+// density2outputs pieces (rendering.py:43-58), shared by composite_kernel, the fused reducer warp and the fp32
+// re-evaluation kernel so that all three round identically
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+__device__ __forceinline__ float alpha_of(float sigma, float dist) {        // 1 - exp(-relu(sigma) * dist)
+  return __fsub_rn(1.f, expf(-__fmul_rn(fmaxf(sigma, 0.f), dist)));
+}
+__device__ __forceinline__ float ray_norm(const float* d) {
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+}
 #endif  // __CUDACC__
 
 }  // namespace s2l

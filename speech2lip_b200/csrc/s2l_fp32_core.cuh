@@ -33,6 +33,10 @@ struct Fp32Args {
   int n_frames;
   long long tiles_per_frame;
   Fp32Program prog;
+  // re-evaluation of listed rays' last samples (src is a RAYS list launch with Sc = 1, s0 = S - 1):
+  const float4* fix_carry;      // [F*R] (T_last, acc rgb) left by the fused compositing epilogue -> fix_rgb [F*R,3] is rewritten
+  float* fix_rgb;
+  float* patch_raw;             // unfused path instead: the exact outputs overwrite raw [F*R, S, 4] at sample S - 1
 };
 
 struct Pipe {

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
   const int tn = tid & 31, m0 = (tid >> 5) * 8;
   const float* Fp = reinterpret_cast<const float*>(a.blob + a.L.off_fp32);
   const float* Cc = reinterpret_cast<const float*>(a.blob + a.L.off_const);
-  const long long n_tiles = a.tiles_per_frame * a.n_frames;
+  const long long n_tiles = a.src.tile_start ? (long long)a.src.tile_start[a.n_frames] : a.tiles_per_frame * a.n_frames;
   const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   Pipe ps{0, my_tiles * a.prog.n_chunks};
   const int E = pe_dim(a.src.uv_dims);
@@ -69,12 +69,13 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
   }
 
   float acc[8][8];
+  int fcur = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int f = (int)(tile / a.tiles_per_frame);
-    const long long p_base = (tile % a.tiles_per_frame) * TM;
+    int f; long long p_base, Pf;
+    tile_locate<TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p_base, Pf);
     // training forward: slot s of `save` is [F*P][256]; this tile's rows start at grow(s)
     const long long n_rows_total = (long long)a.n_frames * a.src.P;
-    const int rows_valid = (int)((a.src.P - p_base) < TM ? (a.src.P - p_base) : TM);
+    const int rows_valid = (int)((Pf - p_base) < TM ? (Pf - p_base) : TM);
     auto grow = [&](int slot) -> float* {
       return a.save ? a.save + ((size_t)slot * n_rows_total + (size_t)f * a.src.P + p_base) * 256 : nullptr;
     };
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
       const int m = tid & 63, part = tid >> 6;   // 4 threads per point, frequencies interleaved
       const long long p = p_base + m;
       float x[3] = {0.f, 0.f, 0.f};
-      if (p < a.src.P) {
+      if (p < Pf) {
         if (ROWLAT) {
           const float* row = a.rows + p * (a.src.uv_dims + kLatent);
           for (int d = 0; d < a.src.uv_dims; ++d) x[d] = row[d];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
       }
       if (ROWLAT) {
         for (int k = part; k < kLatent; k += 4)
-          LAT[k * TMP + m] = (p < a.src.P) ? a.rows[p * (a.src.uv_dims + kLatent) + a.src.uv_dims + k] : 0.f;
+          LAT[k * TMP + m] = (p < Pf) ? a.rows[p * (a.src.uv_dims + kLatent) + a.src.uv_dims + k] : 0.f;
       } else {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256;
         bias0[tid] = fb[tid];
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
     {
       const int m = tid & 63, n = tid >> 6;
       const long long p = p_base + m;
+      float o = 0.f;
       if (n < a.out_ch) {
         const float* w = Fp + F_OUT_W + n * 256;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -167,7 +169,35 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
           s2 = fmaf(X[(k + 2) * TMP + m], __ldg(w + k + 2), s2);
           s3 = fmaf(X[(k + 3) * TMP + m], __ldg(w + k + 3), s3);
         }
-        if (p < a.src.P) a.out[((long long)f * a.src.P + p) * a.out_ch + n] = ((s0 + s1) + (s2 + s3)) + Fp[F_OUT_B + n];
+        o = ((s0 + s1) + (s2 + s3)) + Fp[F_OUT_B + n];
+      }
+      if (!ROWLAT && (a.fix_rgb || a.patch_raw)) {
+        // listed rays (near-zero last-sample density under tensor-core rounding): this exact (r,g,b,sigma) of the
+        // LAST sample either replaces the raw entry (unfused path) or finishes the pixel from the (T_last, acc) pair
+        // the fused compositing epilogue left in `carry`  (rendering.py:43-60 with delta_last = 1e10)
+        if (p < Pf) {
+          const long long gray = (long long)f * a.src.R + a.src.list_rays[(long long)f * a.src.R + p];
+          if (a.patch_raw) {
+            if (n < a.out_ch) a.patch_raw[(gray * a.src.S + (a.src.S - 1)) * 4 + n] = o;
+          } else {
+            PE[n * TMP + m] = o;                       // PE is free after the skip GEMM
+          }
+        }
+        if (a.fix_rgb) {
+          __syncthreads();
+          if (n == 0 && p < Pf) {
+            const int ray = a.src.list_rays[(long long)f * a.src.R + p];
+            const long long gray = (long long)f * a.src.R + ray;
+            const float4 c = a.fix_carry[gray];
+            const float nrm = ray_norm(a.src.rays_d + (a.src.rays_shared ? (long long)ray : gray) * 3);
+            const float w = c.x * alpha_of(PE[3 * TMP + m], __fmul_rn(1e10f, nrm));
+            a.fix_rgb[gray * 3 + 0] = fmaf(w, sigmoidf_acc(PE[0 * TMP + m]), c.y);
+            a.fix_rgb[gray * 3 + 1] = fmaf(w, sigmoidf_acc(PE[1 * TMP + m]), c.z);
+            a.fix_rgb[gray * 3 + 2] = fmaf(w, sigmoidf_acc(PE[2 * TMP + m]), c.w);
+          }
+        }
+      } else if (n < a.out_ch && p < Pf) {
+        a.out[((long long)f * a.src.P + p) * a.out_ch + n] = o;
       }
     }
     __syncthreads();
@@ -197,8 +227,15 @@ static size_t fp32_smem_bytes(bool rowlat) {
 }
 
 int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out,
-                    int out_ch, cudaStream_t st) {
+                    int out_ch, cudaStream_t st, const float4* fix_carry, float* fix_rgb, float* patch_raw) {
   Fp32Args a{};
+  a.fix_carry = fix_carry;
+  a.fix_rgb = fix_rgb;
+  a.patch_raw = patch_raw;
+  if ((fix_rgb || patch_raw) && (src.mode != S2L_PTS_RAYS || !src.list_rays || !src.tile_start || src.Sc != 1 || out_ch != 4)) {
+    set_error("mlp_fp32: the last-sample re-evaluation needs a ray-list launch with Sc = 1 on the out_ch = 4 model");
+    return 2;
+  }
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
   a.src = src;

@@ -48,9 +48,10 @@ constexpr int T1_STAGE = kGranBytes;                // 32 KB: both planes of a g
 constexpr int T1_SM_TCBIAS = SM_STG + T1_NSTG * T1_STAGE;
 constexpr int T1_SM_FBIAS = T1_SM_TCBIAS + kNumG * 256 * 4;
 constexpr int T1_SM_BAR = T1_SM_FBIAS + 2 * 2 * 256 * 4;
-constexpr int T1_NBAR = 2 * T1_NSTG + 2 + 2 + 4 + 4;
+constexpr int T1_NBAR = 2 * T1_NSTG + 2 + 2 + 4 + 4 + 2 + 2;
 constexpr int T1_SM_TMEMPTR = T1_SM_BAR + T1_NBAR * 8;
-constexpr int T1_SMEM_BYTES = T1_SM_TMEMPTR + 16;
+constexpr int T1_SM_RAW = T1_SM_TMEMPTR + 16;          // 2 x [128] float4: output tile handed to the reducer warp
+constexpr int T1_SMEM_BYTES = T1_SM_RAW + 2 * TC_TM * 16;
 static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
 
 // CL = 1: independent CTAs.  CL = 2: CTAs are launched as clusters of two that share ONE weight stream — each CTA
@@ -67,13 +68,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   uint64_t* pe_empty = pe_full + 2;
   uint64_t* acc_full = pe_empty + 2;
   uint64_t* epi_done = acc_full + 4;
+  uint64_t* raw_full = epi_done + 4;
+  uint64_t* raw_empty = raw_full + 2;
+  float4* rawbuf = reinterpret_cast<float4*>(smem + T1_SM_RAW);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + T1_SM_TMEMPTR);
   float* tcbias_s = reinterpret_cast<float*>(smem + T1_SM_TCBIAS);
   float* fbias_s = reinterpret_cast<float*>(smem + T1_SM_FBIAS);   // [2 bufs][2][256]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches and the MMA warp's loop state stay on the uniform datapath
-  const long long n_tiles = a.tiles_per_frame * a.n_frames;
+  const long long n_tiles = launch_tiles(a);
   // every CTA runs the same number of tile iterations (a cluster shares the weight ring, so it must stay in lock step);
   // iterations past the end work on zero rows and store nothing
   const long long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
@@ -98,6 +102,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     for (int b = 0; b < 2; ++b) {
       mbar_init(&pe_full[b], 128);
       mbar_init(&pe_empty[b], 1 + 256);
+      mbar_init(&raw_full[b], 128);
+      mbar_init(&raw_empty[b], 1);
     }
     for (int q = 0; q < 4; ++q) {
       mbar_init(&acc_full[q], 1);
@@ -331,17 +337,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     }
 #undef S2L_IC
 #undef S2L_BC
+  } else if (warp == 3) {
+    // =============================================================== reducer (fused 4-tap blend / alpha compositing)
+    if (a.epi_mode != EPI_RAW) reducer_role(a, n_tiles, tile_end, rawbuf, raw_full, raw_empty, lane);
   } else if (warp >= 4 && warp < 8) {
     // =============================================================== PE producers (one point per thread)
     const int r = tid - 128;
     long long it = 0;
+    int fcur = 0;
     for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      const bool live = tile < n_tiles;
-      const int f = live ? (int)(tile / a.tiles_per_frame) : 0;
-      const long long p = live ? (tile % a.tiles_per_frame) * TC_TM + r : a.src.P;
+      int f; long long p0, Pf;
+      tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
+      const long long p = p0 + r;
       mbar_wait_wd<true>(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
-      pe_write_row<NPASS, UVD>(a.src, f, p, p < a.src.P, r, smem + SM_PE + buf * PE_BUF);
+      pe_write_row<NPASS, UVD>(a.src, f, p, p < Pf, r, smem + SM_PE + buf * PE_BUF);
       {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
         float* dst = fbias_s + buf * 512;
@@ -358,12 +368,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint32_t acc_par[4] = {0, 0, 0, 0};
     int rp = 0;
     long long it = 0;
+    int fcur = 0;
     TL_DECL;
     for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      const bool live = tile < n_tiles;
-      const int f = live ? (int)(tile / a.tiles_per_frame) : 0;
-      const long long p = live ? (tile % a.tiles_per_frame) * TC_TM + row : a.src.P;
+      int f; long long p0, Pf;
+      tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
+      const long long p = p0 + row;
       mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 600 + buf);   // folded per-frame biases staged
       for (int g = 0; g < 8; ++g) {
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
@@ -414,9 +425,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           uint32_t v[4];
           tmem_ld4(d_region + lane_sel, v);
           tmem_ld_wait();
-          if (p < a.src.P) {
+          const float* bo = tcbias_s + 8 * 256;
+          if (a.epi_mode != EPI_RAW) {
+            // hand the tile to the reducer warp (fused 4-tap blend / alpha compositing)
+            mbar_wait_wd(&raw_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 810 + buf);
+            rawbuf[buf * TC_TM + row] = make_float4(__uint_as_float(v[0]) + bo[0], __uint_as_float(v[1]) + bo[1],
+                                                    __uint_as_float(v[2]) + bo[2], __uint_as_float(v[3]) + bo[3]);
+            mbar_arrive(&raw_full[buf]);
+          } else if (p < Pf) {
             float* o = a.out + ((long long)f * a.src.P + p) * a.out_ch;
-            const float* bo = tcbias_s + 8 * 256;
 #pragma unroll
             for (int n = 0; n < 4; ++n)
               if (n < a.out_ch) o[n] = __uint_as_float(v[n]) + bo[n];
@@ -485,6 +502,7 @@ static int launch_tc_cl(const TcArgs& a, long long n_tiles, int npass, int uvd, 
 }
 
 int launch_mlp_tc2(const TcArgs& a, long long n_tiles, int npass, cudaStream_t st);   // s2l_mlp_tc2.cu (CTA pairs)
+void profile_mark(cudaStream_t st, int which);                                         // s2l_capi.cu
 
 // Which tensor-core schedule runs a launch of n_tiles 128-point tiles:
 //   1 = independent CTAs (this file, CL = 1)          2 = CTA pairs, cta_group::2 MMAs sharing every B tile (s2l_mlp_tc2.cu)
@@ -515,7 +533,7 @@ static long long* g_timeline = nullptr;
 extern "C" void s2l_debug_set_timeline(long long* buf) { g_timeline = buf; }     // debug builds (tools/tc_timeline.py)
 
 int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
-                  int npass, cudaStream_t st) {
+                  int npass, cudaStream_t st, const TcEpi* epi) {
   TcArgs a{};
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
@@ -526,10 +544,34 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   a.n_frames = n_frames;
   a.tiles_per_frame = (src.P + TC_TM - 1) / TC_TM;
   a.dbg = g_timeline;
+  if (epi) {
+    a.epi_mode = epi->mode;
+    a.rgb = epi->rgb;
+    a.carry = epi->carry;
+    a.next_count = epi->next_count;
+    a.next_rays = epi->next_rays;
+    a.term_thr = epi->term_thr;
+    a.fix_thr = epi->fix_thr;
+    if (epi->mode == EPI_COMPOSITE && (src.mode != S2L_PTS_RAYS || src.Sc < 4 || (src.Sc & 3) || TC_TM % src.Sc)) {
+      set_error("mlp_tc: fused compositing needs ray mode with a sample-chunk size in {4,8,...,128} (got %d)", src.Sc);
+      return 2;
+    }
+    if (epi->mode == EPI_ENS4 && src.mode != S2L_PTS_GRID_ENS4) { set_error("mlp_tc: fused 4-tap blend needs GRID_ENS4 points"); return 2; }
+  }
+  if (src.list_count && (!src.tile_start || !src.list_rays || !epi || epi->mode != EPI_COMPOSITE)) {
+    set_error("mlp_tc: ray lists need tile_start / list_rays and the fused compositing epilogue");
+    return 2;
+  }
+  // list launches learn their tile count on the device (tile_start[F]); the grid is sized for the upper bound
   const long long n_tiles = a.tiles_per_frame * n_frames;
   if (n_tiles == 0) return 0;
   if (src.uv_dims != 2 && src.uv_dims != 3) { set_error("mlp_tc: unsupported uv_dims %d", src.uv_dims); return 2; }
   const int impl = tc_impl_for(n_tiles);
+  struct ProfScope {       // bench.py's live kernel timing (s2l_profile_enable)
+    cudaStream_t st;
+    explicit ProfScope(cudaStream_t s) : st(s) { profile_mark(st, 0); }
+    ~ProfScope() { profile_mark(st, 1); }
+  } prof_scope(st);
   if (impl == 2) {
     const int r = launch_mlp_tc2(a, n_tiles, npass, st);
     if (r == 0 || tc_forced()) return r;

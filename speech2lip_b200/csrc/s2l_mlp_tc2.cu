@@ -32,9 +32,10 @@ constexpr int T2_SM_BAR = T2_SM_FBIAS + 2 * 2 * 256 * 4;
 // barrier map (64-bit slots): local b_empty[8] pe_full[2] pe_empty[2] acc_full[2] (slots 0-7 unused);
 // leader-side pair barriers pair_full[8] epi_done[4] pe_pair[2]
 constexpr int T2_BEMPTY = 8, T2_PEFULL = 16, T2_PEEMPTY = 18, T2_ACC = 20, T2_PAIRFULL = 22, T2_EPIDONE = 30,
-              T2_PEPAIR = 34, T2_NBAR = 36;
+              T2_PEPAIR = 34, T2_RAWFULL = 36, T2_RAWEMPTY = 38, T2_NBAR = 40;
 constexpr int T2_SM_TMEMPTR = T2_SM_BAR + T2_NBAR * 8;
-constexpr int T2_SMEM_BYTES = T2_SM_TMEMPTR + 16;
+constexpr int T2_SM_RAW = T2_SM_TMEMPTR + 16;          // 2 x [128] float4: output tile handed to the reducer warp
+constexpr int T2_SMEM_BYTES = T2_SM_RAW + 2 * TC_TM * 16;
 static_assert(T2_SMEM_BYTES <= 232448, "shared memory budget");
 
 // waits that must observe writes made by the peer CTA (acquire at cluster scope)
@@ -110,6 +111,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
   uint64_t* pair_full = bars + T2_PAIRFULL;     // used in the leader only
   uint64_t* epi_done = bars + T2_EPIDONE;       // used in the leader only
   uint64_t* pe_pair = bars + T2_PEPAIR;         // used in the leader only
+  uint64_t* raw_full = bars + T2_RAWFULL;
+  uint64_t* raw_empty = bars + T2_RAWEMPTY;
+  float4* rawbuf = reinterpret_cast<float4*>(smem + T2_SM_RAW);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + T2_SM_TMEMPTR);
   float* tcbias_s = reinterpret_cast<float*>(smem + T2_SM_TCBIAS);
   float* fbias_s = reinterpret_cast<float*>(smem + T2_SM_FBIAS);   // [2 bufs][2][256]
@@ -117,7 +121,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform
   const uint32_t rank = cluster_ctarank();
-  const long long n_tiles = a.tiles_per_frame * a.n_frames;
+  const long long n_tiles = launch_tiles(a);
   const long long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;      // same for every CTA: pairs stay in lock step
   const long long tile_end = (long long)blockIdx.x + n_iter * gridDim.x;
   const uint8_t* tcw = a.blob + (NPASS == 2 ? a.L.off_tcw8 : a.L.off_tcw);
@@ -132,6 +136,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       mbar_init(&pe_empty[b], 1 + 256);
       mbar_init(&pe_pair[b], 256);
       mbar_init(&acc_full[b], 1);
+      mbar_init(&raw_full[b], 128);
+      mbar_init(&raw_empty[b], 1);
     }
     for (int q = 0; q < 4; ++q) mbar_init(&epi_done[q], 16);       // one arrive per epilogue warp of either CTA
     fence_barrier_init();
@@ -346,18 +352,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
 #undef S2L_IC
 #undef S2L_BC
     }
+  } else if (warp == 3) {
+    // =============================================================== reducer (fused 4-tap blend / alpha compositing)
+    if (a.epi_mode != EPI_RAW) reducer_role(a, n_tiles, tile_end, rawbuf, raw_full, raw_empty, lane);
   } else if (warp >= 4 && warp < 8) {
     // =============================================================== PE producers (one point per thread)
     const int r = tid - 128;
     const uint32_t pp0 = mapa_u32(smem_u32(&pe_pair[0]), 0);
     long long it = 0;
+    int fcur = 0;
     for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      const bool live = tile < n_tiles;
-      const int f = live ? (int)(tile / a.tiles_per_frame) : 0;
-      const long long p = live ? (tile % a.tiles_per_frame) * TC_TM + r : a.src.P;
+      int f; long long p0, Pf;
+      tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
+      const long long p = p0 + r;
       mbar_wait_wd<true>(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
-      pe_write_row<NPASS, UVD>(a.src, f, p, p < a.src.P, r, smem + SM_PE + buf * PE_BUF);
+      pe_write_row<NPASS, UVD>(a.src, f, p, p < Pf, r, smem + SM_PE + buf * PE_BUF);
       {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
         float* dst = fbias_s + buf * 512;
@@ -376,11 +386,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
     uint32_t acc_par[2] = {0, 0};
     int rp = 0;
     long long it = 0;
+    int fcur = 0;
     for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
-      const bool live = tile < n_tiles;
-      const int f = live ? (int)(tile / a.tiles_per_frame) : 0;
-      const long long p = live ? (tile % a.tiles_per_frame) * TC_TM + row : a.src.P;
+      int f; long long p0, Pf;
+      tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
+      const long long p = p0 + row;
       mbar_wait_wd(&pe_full[buf], (uint32_t)((it >> 1) & 1), 600 + buf);   // folded per-frame biases staged
       for (int g = 0; g < 8; ++g) {
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
@@ -429,9 +440,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
           uint32_t v[4];
           tmem_ld4(d_region + lane_sel, v);
           tmem_ld_wait();
-          if (p < a.src.P) {
+          const float* bo = tcbias_s + 8 * 256;
+          if (a.epi_mode != EPI_RAW) {
+            // hand the tile to the reducer warp (fused 4-tap blend / alpha compositing)
+            mbar_wait_wd(&raw_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 810 + buf);
+            rawbuf[buf * TC_TM + row] = make_float4(__uint_as_float(v[0]) + bo[0], __uint_as_float(v[1]) + bo[1],
+                                                    __uint_as_float(v[2]) + bo[2], __uint_as_float(v[3]) + bo[3]);
+            mbar_arrive(&raw_full[buf]);
+          } else if (p < Pf) {
             float* o = a.out + ((long long)f * a.src.P + p) * a.out_ch;
-            const float* bo = tcbias_s + 8 * 256;
 #pragma unroll
             for (int n = 0; n < 4; ++n)
               if (n < a.out_ch) o[n] = __uint_as_float(v[n]) + bo[n];

@@ -13,14 +13,39 @@ struct PointSrc {
   int rays_shared;
   float eps;            // GRID_ENS4 eps_shift
   const float* eps_pf;  // optional per-frame eps_shift [F]
-  long long P;          // point evaluations per frame
+  long long P;          // point evaluations per frame (RAYS: R * Sc)
   const float* pts;     // EXPLICIT: [F*P, uv_dims]
   const float* rays_o;  // RAYS
   const float* rays_d;
   const float* z;
+  // RAYS, sample chunks and compacted ray lists (early ray termination, the fp32 re-evaluation of near-zero last
+  // samples): a launch evaluates samples [s0, s0 + Sc) of every ray (Sc == S, s0 == 0: whole rays) or of the rays in
+  // a per-frame device list; point p of frame f = sample s0 + p % Sc of ray slot p / Sc.
+  int R;                     // rays per frame (H * W)
+  int s0, Sc;
+  const int* list_count;     // optional [F]: number of rays of frame f in the list (device)
+  const int* list_rays;      // optional [F][R]: ray index within the frame
+  const int* tile_start;     // with a list: [F + 1] first tile of every frame for this kernel's tile size (device)
+};
+
+// Per-pixel reduction fused into the tensor-core kernels' output-layer epilogue (reduce_tile, s2l_tc_common.cuh)
+enum { EPI_RAW = 0, EPI_ENS4 = 1, EPI_COMPOSITE = 2 };
+struct TcEpi {
+  int mode;                  // EPI_*
+  float* rgb;                // [F, H*W, 3]
+  float4* carry;             // EPI_COMPOSITE [F*R]: (T, acc rgb) of a ray between sample chunks / for the fp32 re-evaluation
+  int* next_count;           // list this launch appends to: [F] counts (zeroed by the caller) ...
+  int* next_rays;            // ... and [F][R] ray indices
+  float term_thr, fix_thr;
 };
 
 #ifdef __CUDACC__
+// Ray (index within the frame) that point p of a RAYS launch belongs to.
+__device__ __forceinline__ int ray_of_point(const PointSrc& s, int f, long long p) {
+  const long long slot = p / s.Sc;
+  return s.list_rays ? s.list_rays[(long long)f * s.R + slot] : (int)slot;
+}
+
 // Coordinates of point p (0 <= p < P) of frame f.  Arithmetic mirrors the reference op by op
 // (separate fp32 roundings, no FMA contraction) so that inputs to the PE are bit-identical to what
 // PyTorch computes on the GPU.
@@ -47,16 +72,35 @@ __device__ __forceinline__ void gen_point(const PointSrc& s, int f, long long p,
     x[1] = fminf(fmaxf(v, 0.f), 1.f);
   } else if (s.mode == S2L_PTS_RAYS) {
     // pts = rays_o[:,None,:] + rays_d[:,None,:] * z[...,None]   (NeRF sample placement)
-    const long long ray = p / s.S;
-    const int smp = (int)(p % s.S);
-    const long long rrow = s.rays_shared ? ray : ((long long)f * (s.P / s.S) + ray);
-    const float zz = s.z_per_ray ? s.z[((long long)f * (s.P / s.S) + ray) * s.S + smp] : s.z[smp];
+    const long long ray = ray_of_point(s, f, p);
+    const int smp = s.s0 + (int)(p % s.Sc);
+    const long long rrow = s.rays_shared ? ray : ((long long)f * s.R + ray);
+    const float zz = s.z_per_ray ? s.z[((long long)f * s.R + ray) * s.S + smp] : s.z[smp];
 #pragma unroll
     for (int d = 0; d < 3; ++d)
       x[d] = __fadd_rn(s.rays_o[rrow * 3 + d], __fmul_rn(s.rays_d[rrow * 3 + d], zz));
   } else {
     const float* q = s.pts + ((long long)f * s.P + p) * s.uv_dims;
     for (int d = 0; d < s.uv_dims; ++d) x[d] = q[d];
+  }
+}
+
+// Tile -> (frame, first point, points of that frame in this launch) for a kernel with TMX-point tiles.  Uniform launches
+// have tiles_per_frame tiles in every frame; list launches read the per-frame tile ranges from tile_start (tiles visited
+// by one CTA increase, so `fcur` is a running frame pointer).  Tiles >= n_tiles are dead (Pf = 0).
+template <int TMX>
+__device__ __forceinline__ void tile_locate(const PointSrc& s, long long tiles_per_frame, long long n_tiles, long long tile,
+                                            int& fcur, int& f, long long& p0, long long& Pf) {
+  if (tile >= n_tiles) { f = 0; p0 = 0; Pf = 0; return; }
+  if (s.tile_start) {
+    while (tile >= s.tile_start[fcur + 1]) ++fcur;
+    f = fcur;
+    p0 = (tile - s.tile_start[f]) * TMX;
+    Pf = (long long)s.list_count[f] * s.Sc;
+  } else {
+    f = (int)(tile / tiles_per_frame);
+    p0 = (tile % tiles_per_frame) * TMX;
+    Pf = s.P;
   }
 }
 

@@ -38,8 +38,6 @@ __global__ void ensemble4_blend_kernel(const float* __restrict__ raw, PointSrc s
   for (int c = 0; c < 3; ++c) rgb[gid * 3 + c] = acc[c];
 }
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
-
 // One warp per ray.  weights_i = alpha_i * prod_{j<i} (1 - alpha_j + 1e-10); rgb = sum w*sigmoid(c); depth = sum w*z.
 __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ raw, const float* __restrict__ z_vals,
                                                         int z_per_ray, const float* __restrict__ rays_d,
@@ -142,6 +140,71 @@ __global__ void frames_to_bgr8_kernel(const float* __restrict__ rgb, long long n
   bgr[gid * 3 + 0] = o[0];
   bgr[gid * 3 + 1] = o[1];
   bgr[gid * 3 + 2] = o[2];
+}
+
+// Per-frame tile ranges of a compacted ray list: ts[f] = sum_{g<f} ceil(count[g] * Sc / T) for T = 128 (tensor-core
+// kernels) and T = 64 (fp32 kernel); ts[F] = the launch's tile count, read by the persistent kernels on the device so
+// that no host synchronisation sits between the launch that builds a list and the launch that consumes it.
+__global__ void __launch_bounds__(256) tile_scan_kernel(const int* __restrict__ count, int F, int Sc, int* __restrict__ ts128,
+                                                        int* __restrict__ ts64) {
+  __shared__ int part[2][256];
+  const int t = threadIdx.x;
+  const int per = (F + 255) / 256;
+  const int lo = min(t * per, F), hi = min(lo + per, F);
+  int s128 = 0, s64 = 0;
+  for (int f = lo; f < hi; ++f) {
+    const long long pts = (long long)count[f] * Sc;
+    s128 += (int)((pts + 127) / 128);
+    s64 += (int)((pts + 63) / 64);
+  }
+  part[0][t] = s128;
+  part[1][t] = s64;
+  __syncthreads();
+  if (t == 0) {
+    int a128 = 0, a64 = 0;
+    for (int i = 0; i < 256; ++i) {
+      const int v128 = part[0][i], v64 = part[1][i];
+      part[0][i] = a128;
+      part[1][i] = a64;
+      a128 += v128;
+      a64 += v64;
+    }
+    ts128[F] = a128;
+    ts64[F] = a64;
+  }
+  __syncthreads();
+  s128 = part[0][t];
+  s64 = part[1][t];
+  for (int f = lo; f < hi; ++f) {
+    ts128[f] = s128;
+    ts64[f] = s64;
+    const long long pts = (long long)count[f] * Sc;
+    s128 += (int)((pts + 127) / 128);
+    s64 += (int)((pts + 63) / 64);
+  }
+}
+
+// Unfused volumetric path: list the rays whose last-sample density (raw[ray, S-1, 3]) is within thr of zero.
+__global__ void flag_last_kernel(const float* __restrict__ raw, int F, int R, int S, float thr, int* __restrict__ count,
+                                 int* __restrict__ rays) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)F * R) return;
+  const float sg = raw[(gid * S + (S - 1)) * 4 + 3];
+  if (fabsf(sg) < thr) {
+    const int f = (int)(gid / R);
+    const int slot = atomicAdd(count + f, 1);
+    rays[(long long)f * R + slot] = (int)(gid % R);
+  }
+}
+
+int launch_tile_scan(const int* count, int F, int Sc, int* ts128, int* ts64, cudaStream_t st) {
+  tile_scan_kernel<<<1, 256, 0, st>>>(count, F, Sc, ts128, ts64);
+  return check_launch("tile_scan_kernel") ? 0 : 5;
+}
+int launch_flag_last(const float* raw, int F, int R, int S, float thr, int* count, int* rays, cudaStream_t st) {
+  const long long n = (long long)F * R;
+  flag_last_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, F, R, S, thr, count, rays);
+  return check_launch("flag_last_kernel") ? 0 : 5;
 }
 
 }  // namespace s2l

@@ -36,7 +36,21 @@ struct TcArgs {
   int n_frames;
   long long tiles_per_frame;
   long long* dbg;            // S2L_TIMELINE builds only: event log of CTA 0 (tools/tc_timeline.py)
+  // ---- fused per-pixel reduction (the reducer warp, reduce_tile below)
+  int epi_mode;              // EPI_RAW: raw outputs -> out;  EPI_ENS4: 4-tap blend -> rgb;  EPI_COMPOSITE: alpha compositing -> rgb
+  float* rgb;                // [F, H*W, 3]
+  float4* carry;             // EPI_COMPOSITE [F*R]: (T, acc rgb) of a ray between sample chunks / for the fp32 re-evaluation
+  int* next_count;           // EPI_COMPOSITE: per-frame list this launch appends to ([F] counts, zeroed by the host side) ...
+  int* next_rays;            // ... [F][R] ray indices: rays still alive after a non-final chunk, or (final chunk) rays
+                             //     whose last-sample density is too close to zero to trust the tensor-core sign
+  float term_thr;            // non-final chunk: a ray whose transmittance fell below term_thr is finished
+  float fix_thr;             // final chunk: |sigma_last| < fix_thr -> listed for the fp32 re-evaluation (0: never)
 };
+
+
+__device__ __forceinline__ long long launch_tiles(const TcArgs& a) {
+  return a.src.tile_start ? (long long)a.src.tile_start[a.n_frames] : a.tiles_per_frame * a.n_frames;
+}
 
 // Cycle-stamped event log for pipeline analysis; compiled out unless -DS2L_TIMELINE.
 #ifdef S2L_TIMELINE
@@ -393,6 +407,146 @@ __device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long lo
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
     if (NPASS == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
+  }
+}
+
+// ------------------------------------------------------------------ fused per-pixel reductions (reducer warp)
+// The output-layer epilogue hands the tile's 128 raw outputs (float4 per point) to ONE otherwise idle warp through a
+// double-buffered shared-memory tile; that warp does the per-pixel reduction off the MMA / epilogue critical path:
+//   EPI_ENS4      4 taps -> 1 pixel (Trainer.predict_lip_image, training.py:237-249); lane = pixel
+//   EPI_COMPOSITE density2outputs (rendering.py:43-60): lane = 4 consecutive samples of one ray, segmented shuffle scan
+//                 of the transmittance over the Sc/4 lanes of a ray (Sc | 128, 4 | Sc: rays never straddle tiles).
+// so the raw [P,4] tensor never exists in HBM.  With sample chunks (s0, Sc < S) the (T, acc) pair of a ray is carried
+// through `carry`, rays whose transmittance fell below term_thr are finished early (early ray termination: the
+// remaining samples would change the pixel by < term_thr) and the survivors are appended to the next launch's list.
+// On the final chunk rays whose last-sample density is within fix_thr of zero are listed for the fp32 re-evaluation
+// (rendering.py:44 gives the last sample delta = 1e10: alpha_last is a step function of sign(sigma_last), so a
+// tensor-core rounding error there flips the pixel; the exact kernel redoes those few rays, s2l_mlp_fp32.cu).
+__device__ __forceinline__ void reduce_tile(const TcArgs& a, int f, long long p0, long long Pf, const float4* rawbuf, int lane) {
+  const PointSrc& s = a.src;
+  const long long p = p0 + 4 * lane;
+  const bool valid = p < Pf;
+  if (a.epi_mode == EPI_ENS4) {
+    if (!valid) return;
+    const long long pix = p >> 2;
+    const int px = (int)(pix % s.W), py = (int)(pix / s.W);
+    const float u0 = linspace01(px, s.W), v0 = linspace01(py, s.H);
+    float area[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float x[3];
+      gen_point(s, f, p + t, x);
+      area[t] = ens4_area(x[0], x[1], u0, v0);
+    }
+    const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float w = __fdiv_rn(area[3 - t], tot);       // areas 0<->3, 1<->2 swapped (training.py:243-245)
+      const float4 v = rawbuf[4 * lane + t];
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(v.x, w));
+      acc[1] = __fadd_rn(acc[1], __fmul_rn(v.y, w));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(v.z, w));
+    }
+    float* o = a.rgb + ((long long)f * s.H * s.W + pix) * 3;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+    return;
+  }
+  // ---- EPI_COMPOSITE
+  const int L = s.Sc >> 2;                 // lanes per ray: 1, 2, 4, ..., 32
+  const int sub = lane & (L - 1);
+  float Tl = 1.f, A0 = 0.f, A1 = 0.f, A2 = 0.f;
+  float a_last = 0.f, T_before = 1.f, sig_last = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
+  float Tin = 1.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
+  int ray = 0;
+  bool has_last = false;
+  if (valid) {
+    ray = ray_of_point(s, f, p);
+    const long long gray = (long long)f * s.R + ray;
+    const int smp = s.s0 + (int)(p % s.Sc);
+    const float nrm = ray_norm(s.rays_d + (s.rays_shared ? (long long)ray : gray) * 3);
+    const float* zr = s.z_per_ray ? s.z + gray * s.S : s.z;
+    if (s.s0 > 0) {
+      const float4 c = a.carry[gray];
+      Tin = c.x; B0 = c.y; B1 = c.z; B2 = c.w;
+    }
+    has_last = (smp + 4 == s.S);
+    float zc = zr[smp];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = rawbuf[4 * lane + i];
+      float dist;
+      if (smp + i + 1 < s.S) {
+        const float zn = zr[smp + i + 1];
+        dist = __fmul_rn(__fsub_rn(zn, zc), nrm);
+        zc = zn;
+      } else {
+        dist = __fmul_rn(1e10f, nrm);
+      }
+      const float alpha = alpha_of(v.w, dist);
+      const float c0 = sigmoidf_acc(v.x), c1 = sigmoidf_acc(v.y), c2 = sigmoidf_acc(v.z);
+      if (has_last && i == 3) {
+        a_last = alpha; T_before = Tl; sig_last = v.w; l0 = c0; l1 = c1; l2 = c2;
+      } else {
+        const float w = alpha * Tl;
+        A0 = fmaf(w, c0, A0); A1 = fmaf(w, c1, A1); A2 = fmaf(w, c2, A2);
+      }
+      Tl *= __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+    }
+  }
+  float incl = Tl;
+  for (int o = 1; o < L; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (sub >= o) incl *= up;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (sub == 0) excl = 1.f;
+  const float C = Tin * excl;              // transmittance in front of this lane's first sample
+  float S0 = C * A0, S1 = C * A1, S2 = C * A2;
+  for (int o = 1; o < L; o <<= 1) {
+    S0 += __shfl_xor_sync(0xffffffffu, S0, o);
+    S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+    S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+  }
+  if (!valid || sub != L - 1) return;
+  const long long gray = (long long)f * s.R + ray;
+  float* o = a.rgb + gray * 3;
+  const float acc0 = B0 + S0, acc1 = B1 + S1, acc2 = B2 + S2;
+  if (has_last) {
+    const float T_last = C * T_before;
+    const float w = T_last * a_last;
+    o[0] = fmaf(w, l0, acc0); o[1] = fmaf(w, l1, acc1); o[2] = fmaf(w, l2, acc2);
+    if (a.fix_thr > 0.f && fabsf(sig_last) < a.fix_thr) {
+      a.carry[gray] = make_float4(T_last, acc0, acc1, acc2);
+      const int slot = atomicAdd(a.next_count + f, 1);
+      a.next_rays[(long long)f * s.R + slot] = ray;
+    }
+  } else {
+    const float T_end = Tin * incl;
+    if (T_end < a.term_thr) {
+      o[0] = acc0; o[1] = acc1; o[2] = acc2;             // terminated: what is left of the ray weighs < term_thr
+    } else {
+      a.carry[gray] = make_float4(T_end, acc0, acc1, acc2);
+      const int slot = atomicAdd(a.next_count + f, 1);
+      a.next_rays[(long long)f * s.R + slot] = ray;
+    }
+  }
+}
+
+// The reducer warp's loop, shared by both tensor-core kernels (raw_full: 128 arrivals from the output-layer epilogue
+// threads, raw_empty: one arrival from the reducer).
+__device__ __forceinline__ void reducer_role(const TcArgs& a, long long n_tiles, long long tile_end, const float4* rawbuf,
+                                             uint64_t* raw_full, uint64_t* raw_empty, int lane) {
+  long long it = 0;
+  int fcur = 0;
+  for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
+    const int buf = (int)(it & 1);
+    int f; long long p0, Pf;
+    tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
+    mbar_wait_wd(&raw_full[buf], (uint32_t)((it >> 1) & 1), 900 + buf);
+    reduce_tile(a, f, p0, Pf, rawbuf + buf * TC_TM, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&raw_empty[buf]);
   }
 }
 

@@ -258,14 +258,15 @@ class LipRenderer:
         self.precision = precision
         self._scratch = None
 
-    def _scratch_for(self, geom, device):
-        need = _cabi.lib().s2l_render_scratch_bytes(C.byref(geom))
+    def _scratch_for(self, geom, device, prec, want_aux):
+        need = _cabi.lib().s2l_render_scratch_bytes(C.byref(geom), prec, 1 if want_aux else 0)
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != device:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=device)
         return self._scratch
 
     def render_frames(self, audio, index, H, W, mode="plain", eps_shift=0.0, n_samples=None, rays_o=None,
-                      rays_d=None, z_vals=None, out=None, return_aux=False, precision=None):
+                      rays_d=None, z_vals=None, out=None, return_aux=False, precision=None, sample_chunks=1, term_thr=0.0,
+                      fix_thr=0.0):
         lib = _cabi.lib()
         audio = _f32c(audio, "audio")
         if audio.dim() != 3 or tuple(audio.shape[1:]) != (16, 29):
@@ -284,7 +285,8 @@ class LipRenderer:
             eps_shift = 0.0
         g = S2LGeom(n_frames=F, height=H, width=W, n_samples=0, pts_mode=_cabi.PTS_GRID, uv_dims=self.w.uv_dims,
                     out_ch=self.w.out_ch, z_per_ray=0, rays_per_frame_shared=0, pts_per_frame=0, eps_shift=float(eps_shift),
-                    eps_per_frame=None if eps_pf is None else eps_pf.data_ptr())
+                    eps_per_frame=None if eps_pf is None else eps_pf.data_ptr(), sample_chunks=int(sample_chunks),
+                    term_thr=float(term_thr), fix_thr=float(fix_thr))
         weights = depth = None
         if mode == "plain":
             g.pts_mode = _cabi.PTS_GRID
@@ -330,7 +332,8 @@ class LipRenderer:
             _need_cuda(out, "out")
             if tuple(out.shape) != (F, H, W, 3) or out.dtype != torch.float32 or not out.is_contiguous():
                 raise ValueError("out must be a contiguous fp32 [F,H,W,3] tensor")
-        scratch = self._scratch_for(g, dev)
+        scratch = self._scratch_for(g, dev, prec, return_aux)
+        self._last_geom = g
         with torch.cuda.device(dev):
             _cabi.check(lib.s2l_render_frames(_ptr(self.w.blob), C.byref(g), _ptr(audio), _ptr(idx), _ptr(rays_o),
                                               _ptr(rays_d), _ptr(z_vals), _ptr(out), _ptr(weights), _ptr(depth),
@@ -338,6 +341,18 @@ class LipRenderer:
         if return_aux:
             return out, weights, depth
         return out
+
+    def last_render_counts(self):
+        """Counters the last volumetric render left in the scratch buffer (one host sync): {"alive": [C-1][F] rays of each
+        frame still alive when sample chunk k = 1..C-1 started (early ray termination), "reevaluated": [F] rays whose last
+        sample was re-evaluated in fp32 (near-zero density, include/speech2lip_b200.h fix_thr)}."""
+        g = self.__dict__.get("_last_geom")
+        if g is None or g.pts_mode != _cabi.PTS_RAYS or self._scratch is None:
+            raise RuntimeError("no volumetric render has run on this renderer")
+        off = _cabi.lib().s2l_render_counts_offset(C.byref(g))
+        Cn, F = max(int(g.sample_chunks), 1), int(g.n_frames)
+        cnt = self._scratch[off:off + (Cn + 1) * F * 4].view(torch.int32).view(Cn + 1, F).cpu()
+        return {"alive": cnt[1:Cn], "reevaluated": cnt[Cn]}
 
     def render_sync_window(self, audio_window, index, total_frame, H, W, eps_shift):
         """The sync-expert loss window (training.py:500-525): T consecutive lip frames, each through the 4-tap

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libs2l_b200.so does not export %s" % n
     assert sorted(_cabi.SYMBOLS) == names, "binding table and header disagree"
-    assert lib.s2l_abi_version() == 1
+    assert lib.s2l_abi_version() == 2
 
 
 def test_param_order_matches_header_enum():
