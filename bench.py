@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
-    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays in the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=0, help="bound the CPU steps to this many rays of a frame (0 = whole frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -64,20 +64,52 @@ def points_per_frame(a):
     return n * (a.samples if a.mode == "volumetric" else 4 if a.mode == "ensemble4" else 1)
 
 
-# --------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(a, threads):
-    """Times the oracle port (reference arithmetic, torch CPU fp32, no_grad) on a bounded sample of the
-    workload and extrapolates to frames/s.  Sample = `cpu_rays` rays (x samples) of one frame, including
-    AudioNet once and compositing — i.e. cpu_rays/(size*size) of a frame."""
+# --------------------------------------------------------------------------------------------- reference arm
+def reference_runner(a, device, n_rays=None):
+    """One step of the workload on the REFERENCE'S OWN CODE (oracle/ref_runner.py: the unmodified TalkingFace / get_rays /
+    density2outputs / inference-loop body imported from oracle/_ref), or — only if that copy is absent — on the oracle port.
+    Returns (run() -> rgb of ONE frame or of its first n_rays rays, fraction of a frame per run, description, kind)."""
+    from oracle import ref_runner as RR
+    from oracle import synth
+    H = W = a.size
+    audio = torch.from_numpy(synth.make_audio(1, seed=1))
+    if not RR.available():
+        return oracle_port_runner(a, n_rays) + ("port",)
+    if a.mode == "volumetric":
+        m = RR.model(3, 4, device)
+        c2w = torch.eye(4)[:3]
+        n = H * W if n_rays is None else min(n_rays, H * W)
+
+        def run():
+            return RR.render_volumetric(m, audio, 0, H, W, a.samples, 1200.0, c2w, device, n_rays=None if n == H * W else n)
+        desc = "%d of %d rays x %d samples of one frame: TalkingFace(uv_dims=3,output_ch=4).audio_merge_forward once, rgb_forward in " \
+               "65536-point calls, get_rays, density2outputs" % (n, H * W, a.samples)
+        return run, n / float(H * W), desc, "reference"
+    m = RR.model(2, 3, device)
+    n_rows = H if n_rays is None else max(1, min(H, n_rays // W))
+    if a.mode == "plain":
+        def run():
+            return RR.render_plain(m, audio, 0, H, W, device, n_rows=None if n_rows == H else n_rows)
+        desc = "%d of %d pixel rows of one frame through the loop body of inference.py:144-159 as written (window tiled per pixel)" % (n_rows, H)
+        return run, n_rows / float(H), desc, "reference"
+    tr = RR.trainer(m, device, n_rows, W)
+
+    def run():
+        with torch.no_grad():
+            return RR.render_ensemble4(tr, audio, 0, n_rows, W, device)
+    return run, n_rows / float(H), "%d of %d pixel rows of one frame through Trainer.predict_lip_image (training.py:158-251)" % (n_rows, H), "reference"
+
+
+def oracle_port_runner(a, n_rays):
+    """Fallback when oracle/_ref is missing: the oracle port (restated reference arithmetic, torch CPU)."""
     from oracle import s2l_oracle as O
     from oracle import synth
-    torch.set_num_threads(threads)
     H = W = a.size
     audio = torch.from_numpy(synth.make_audio(1, seed=1))
     if a.mode == "volumetric":
         sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming", 3, 4))
         ro, rd = O.get_rays(H, W, 1200.0, torch.eye(4)[:3])
-        n = min(a.cpu_rays, H * W)
+        n = H * W if n_rays is None else min(n_rays, H * W)
         ro, rd = ro.reshape(-1, 3)[:n], rd.reshape(-1, 3)[:n]
         z = O.z_samples(a.samples)
 
@@ -91,29 +123,28 @@ def cpu_sample(a, threads):
                     outs.append(O.rgb_forward(sd, torch.cat([p, lat.expand(p.shape[0], -1)], -1), torch.tensor([0]), uv_dims=3))
                 raw = torch.cat(outs).reshape(n, a.samples, 4)
                 return O.density2outputs(raw, z.expand(n, a.samples), rd)[0]
-        frac = n / float(H * W)
-        desc = "%d of %d rays x %d samples of one frame (AudioNet once + MLP in 65536-point chunks + compositing)" % (n, H * W, a.samples)
-    else:
-        sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming", 2, 3))
-        n_rows = max(1, min(H, a.cpu_rays // W))
+        return run, n / float(H * W), "oracle port, %d of %d rays x %d samples of one frame" % (n, H * W, a.samples)
+    sd = O.to_torch_sd(synth.make_state_dict(0, "kaiming", 2, 3))
+    n_rows = H if n_rays is None else max(1, min(H, n_rays // W))
 
-        def run():
-            with torch.no_grad():
-                if a.mode == "plain":
-                    return O.render_plain(sd, audio, 0, n_rows, W)
-                return O.render_ensemble4(sd, audio, 0, n_rows, W, 0.0)
-        frac = n_rows / float(H)
-        desc = "%d of %d pixel rows of one frame, mode %s" % (n_rows, H, a.mode)
-    return run, frac, desc
+    def run():
+        with torch.no_grad():
+            if a.mode == "plain":
+                return O.render_plain(sd, audio, 0, n_rows, W)
+            return O.render_ensemble4(sd, audio, 0, n_rows, W, 0.0)
+    return run, n_rows / float(H), "oracle port, %d of %d pixel rows of one frame, mode %s" % (n_rows, H, a.mode)
 
 
 def run_reference_arm(a):
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores; each step = ONE WHOLE
+    frame of the workload (no extrapolation) unless --cpu-rays bounds it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    run, frac, desc = cpu_sample(a, threads)
-    for _ in range(max(1, min(a.warmup, 2))):
+    torch.set_num_threads(threads)
+    run, frac, desc, kind = reference_runner(a, torch.device("cpu"), a.cpu_rays if a.cpu_rays > 0 else None)
+    for _ in range(max(1, min(a.warmup, 1))):
         run()
     t0 = time.perf_counter()
     for _ in range(a.steps):
@@ -122,12 +153,13 @@ def run_reference_arm(a):
     fps = frac / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "reference_arm": "oracle port of the reference's PyTorch CPU path "
-                   "(the reference is pure Python with no installable package; /root/reference is absent on this box)"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "each step = " + desc + "; frames/s extrapolated by the sampled fraction"},
+        "config": {"workload": workload_name(a), "mode": a.mode,
+                   "reference_arm": "the reference's own modules (unmodified copy in oracle/_ref, oracle/build_ref.py) on the host cores, "
+                                    "torch CPU fp32, no_grad" if kind == "reference" else "oracle port (oracle/_ref missing on this box)",
+                   "frames_per_step": frac},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": "each step = " + desc},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -432,17 +464,17 @@ def run_gpu_arm(a):
         if world == 1 and not a.no_extras:
             line["extras"] = extras
         if world == 1 and not a.no_cpu_baseline:
+            # the reference's own code on this box's host cores: a 4096-ray warm-up, then ONE whole frame (about 10-20 s)
             threads = os.cpu_count() or 1
-            run, frac, desc = cpu_sample(a, threads)
-            run()
+            torch.set_num_threads(threads)
+            warm, _, _, _ = reference_runner(a, torch.device("cpu"), 4096)
+            warm()
+            run, frac, desc, kind = reference_runner(a, torch.device("cpu"), a.cpu_rays if a.cpu_rays > 0 else None)
             t0 = time.perf_counter()
-            reps = 0
-            while reps < 3 and (reps == 0 or time.perf_counter() - t0 < 20.0):
-                run()
-                reps += 1
-            dt = (time.perf_counter() - t0) / reps
-            line["cpu_baseline"] = {"value": frac / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-                                    "sample": desc + "; %d repetitions, frames/s extrapolated by the sampled fraction" % reps}
+            run()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": frac / dt, "unit": "frames/s", "cores": threads, "kind": kind,
+                                    "sample": desc + "; one timed repetition after a 4096-ray warm-up"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — import shim for the *real* reference implementation.
 
-This file is used only in the build container (where /root/reference is mounted)
-to (a) validate oracle/s2l_oracle.py against the reference's own code and
-(b) generate the golden vectors committed under tests/golden/.  It never runs on
-the GPU box and is never imported by the product package.
+It imports the reference's own code from /root/reference (build container) or, where that does not exist (the GPU
+box), from the unmodified copy oracle/build_ref.py vendored into oracle/_ref/ (git-ignored), to
+(a) validate oracle/s2l_oracle.py against the reference's own code, (b) generate the golden vectors committed under
+tests/golden/, (c) run the reference itself as bench.py's CPU / eager-GPU baselines and (d) drive the reference's own
+callers against the drop-in in tests/.  It is never imported by the product package.
 
 Recipe follows SURVEY.md §8(c): the reference's import chain pulls packages that
 are not installed (lpips, imageio, librosa, flowlib->png, matplotlib) but that
@@ -13,7 +14,8 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("S2L_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = os.environ.get("S2L_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/src") else _VENDORED)
 
 
 def reference_available() -> bool:

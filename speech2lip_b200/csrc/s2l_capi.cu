@@ -223,12 +223,13 @@ static RenderPlan make_plan(const S2LGeom& g, int precision, bool want_aux) {
   size_t o = 0;
   p.off_bias = o;   o = al(o + F * 4 * 256 * sizeof(float));
   const bool lists = rays && p.tc && (p.fix || p.chunks > 1);
+  // the counters come first so that their offset does not depend on which sections follow (s2l_render_counts_offset)
+  p.off_counts = o; if (rays) o = al(o + (size_t)(p.chunks + 1) * F * sizeof(int));
+  p.off_ts128 = o;  if (lists) o = al(o + (F + 1) * sizeof(int));
+  p.off_ts64 = o;   if (lists) o = al(o + (F + 1) * sizeof(int));
   p.off_carry = o;  if (lists && p.fused) o = al(o + F * R * sizeof(float4));
   p.off_list[0] = o; if (lists) o = al(o + F * R * sizeof(int));
   p.off_list[1] = o; if (lists && p.chunks > 1) o = al(o + F * R * sizeof(int));
-  p.off_counts = o; if (lists) o = al(o + (size_t)(p.chunks + 1) * F * sizeof(int));
-  p.off_ts128 = o;  if (lists) o = al(o + (F + 1) * sizeof(int));
-  p.off_ts64 = o;   if (lists) o = al(o + (F + 1) * sizeof(int));
   p.off_raw = o;
   const bool direct = (g.pts_mode == S2L_PTS_GRID && g.out_ch == 3);
   if (!p.fused && !direct && P > 0) o = al(o + F * (size_t)P * g.out_ch * sizeof(float));
@@ -295,8 +296,7 @@ extern "C" int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, cons
   }
 
   // ---- RAYS
-  const bool lists_used = pl.tc && (pl.fix || pl.chunks > 1);
-  if (lists_used && cudaMemsetAsync(counts, 0, (size_t)(pl.chunks + 1) * F * sizeof(int), st) != cudaSuccess) {
+  if (cudaMemsetAsync(counts, 0, (size_t)(pl.chunks + 1) * F * sizeof(int), st) != cudaSuccess) {
     set_error("s2l_render_frames: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
     return 5;
   }
