@@ -146,7 +146,7 @@ def test_synth_generators_are_shared_not_duplicated():
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         for node in ast.walk(fn):
             if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
-                assert fn.name == "cpu_sample", "bench.py imports oracle/ in %s()" % fn.name
+                assert fn.name in ("reference_runner", "oracle_port_runner", "eager_gpu_reference"), "bench.py imports oracle/ in %s()" % fn.name
     for node in tree.body:
         assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node)), "module-level oracle import"
 
@@ -163,10 +163,11 @@ def test_bench_constants_and_traffic_helper_cpu():
     assert b.FLOP_PER_POINT["plain"] == 2 * (2 * 42 * 256 + 5 * 256 * 256 + 512 * 256 + 2 * 256 * 256 + 256 * 3)
     # folded program: G0 64x256, G1-4, G5 (64+256)x256, G6-7, G8 256x16
     assert b.ISSUED_MAC_PER_POINT == 64 * 256 + 4 * 256 * 256 + 320 * 256 + 2 * 256 * 256 + 256 * 16
-    t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-    one = b.ncu_traffic(t["frames_per_launch"], t["points_per_launch"])
-    assert one == t["dram_bytes_read"] + t["dram_bytes_write"]
-    assert abs(b.ncu_traffic(8, t["points_per_launch"]) - 8 * one) < 1e-6 * one
+    # the traffic figure is only reported for a geometry that was actually captured (no scaling between launch sizes)
+    t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[0]
+    assert t["frames_per_launch"] == 8 and t["points_per_launch"] == 8 * 256 * 256 * 64 and t["fused_epilogue"]
+    assert b.ncu_traffic(8, 256 * 256 * 64, t["precision"]) == t["dram_bytes_read"] + t["dram_bytes_write"]
+    assert b.ncu_traffic(1, 256 * 256 * 64, t["precision"]) is None and b.ncu_traffic(8, 256 * 256 * 64, "bf16x1") is None
 
 
 def test_drop_in_helper_entry_points_report_errors():
