@@ -135,6 +135,38 @@ def oracle_port_runner(a, n_rays):
     return run, n_rows / float(H), "oracle port, %d of %d pixel rows of one frame, mode %s" % (n_rows, H, a.mode)
 
 
+def eager_gpu_reference(a, dev):
+    """the reference's own modules in PyTorch eager fp32 on THIS GPU (TF32 off) — the number a user of the
+    reference sees on a B200.  One whole frame per repetition, wall clock around synchronised repetitions."""
+    from oracle import ref_runner as RR
+    import copy
+    out = {}
+    if not RR.available():
+        return {"reference_gpu_eager": {"error": "oracle/_ref missing", "frames_per_s": 0.0, "ms_per_step": 0.0}}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for mode in ("volumetric", "plain", "ensemble4"):
+            b = copy.copy(a)
+            b.mode = mode
+            run, frac, desc, kind = reference_runner(b, dev, None)
+            run()
+            torch.cuda.synchronize()
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                run()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            out["reference_gpu_eager_%s_%dx%d" % (mode, a.size, a.size)] = {
+                "frames_per_s": frac / dt, "ms_per_step": dt * 1e3, "frames_per_step": frac, "kind": kind,
+                "what": "reference modules, PyTorch eager fp32 (TF32 off) on this GPU: " + desc}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return out
+
+
 def run_reference_arm(a):
     """`--impl reference`: the reference's own CPU implementation of the path on all host cores; each step = ONE WHOLE
     frame of the workload (no extrapolation) unless --cpu-rays bounds it."""
@@ -411,6 +443,10 @@ def run_gpu_arm(a):
                                                               "what": "inference.py:144-159 call sequence through TalkingFace, wall clock incl. Python"}
         except Exception as e:      # an extra must never take the headline line down
             extras["drop_in_inference_loop"] = {"error": str(e)[:200], "frames_per_s": 0.0, "ms_per_step": 0.0}
+        try:
+            extras.update(eager_gpu_reference(a, dev))
+        except Exception as e:
+            extras["reference_gpu_eager"] = {"error": str(e)[:200], "frames_per_s": 0.0, "ms_per_step": 0.0}
 
     t = torch.tensor([dev_ms, e2e_ms, ker_ms], device=dev, dtype=torch.float64)
     if world > 1:

@@ -257,8 +257,12 @@ class TalkingFace(nn.Module):
             return None
         shifted_ds = any(s in self.data_path for s in ('macron', 'obama_adnerf', 'obama2_face_crop', 'may'))
         aug = use_post_fusion_blackaug and random.random() > 0.5        # same RNG draw as tf_nerf.py:369
-        if rgb_lip_warped.is_cuda and not aug:
-            # fused gather-blend kernel; the UNet stays cuDNN
+        needs_grad = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad
+                                                     for t in (rgb_lip_warped, rgb_face_canonical, rgb_gt, coord))
+        if rgb_lip_warped.is_cuda and not aug and not needs_grad:
+            # fused gather-blend kernel; the UNet stays cuDNN.  The kernel's outputs carry no grad_fn,
+            # so whenever a gradient has to reach the lip MLP (training.py:436-445, 525-539) the differentiable branch
+            # below runs instead.
             lw_ = rgb_lip_warped.shape[2]
             pad_ = -1
             if self.expand_lip_mask:
@@ -289,7 +293,7 @@ class TalkingFace(nn.Module):
             face_obs = (face_obs == 1).float()
 
             def holes(ref):
-                keep = (torch.randn(ref.shape, device=ref.device)[:, :1] >= 0.000001).float()
+                keep = (torch.randn(ref.shape).to(ref.device)[:, :1] >= 0.000001).float()    # CPU draw, as tf_nerf.py:309
                 keep = keep * face_obs + (1 - face_obs)
                 return (keep != 0).float()
 

@@ -30,6 +30,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.s2l_abi_version() == 2
 
 
+def test_integration_md_struct_stub_matches_the_binding():
+    """INTEGRATION.md shows the ctypes S2LGeom a reference maintainer would write; it must list exactly the binding's
+    fields (a stub 8 bytes short once handed the kernels a garbage eps_per_frame pointer), and both must have the size
+    the compiled library reports."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class S2LGeom(C.Structure)"):doc.index("assert lib.s2l_sizeof_geom()")]
+    names = re.findall(r'\("([a-z0-9_]+)", C\.c_', stub)
+    assert names == [n for n, _ in _cabi.S2LGeom._fields_]
+    types_ = re.findall(r'\("[a-z0-9_]+", C\.(c_[a-z0-9_]+)\)', stub)
+    assert [getattr(C, t) for t in types_] == [t for _, t in _cabi.S2LGeom._fields_]
+    assert _cabi.lib().s2l_sizeof_geom() == C.sizeof(_cabi.S2LGeom)
+
+
 def test_param_order_matches_header_enum():
     src = open(os.path.join(ROOT, "include", "speech2lip_b200.h")).read()
     assert "S2L_NUM_PARAMS" in src

@@ -1,0 +1,216 @@
+"""GPU tests that run the REFERENCE'S OWN CALLERS against the drop-in: the reference package (imported through
+oracle/ref_shim.py from /root/reference or the vendored oracle/_ref) gets `TalkingFace` replaced by
+speech2lip_b200.TalkingFace exactly where the reference binds it (src/face_simple/config.py:10, src/face_simple/models),
+and then its own code drives the model:
+  * Trainer.predict_lip_image                         (src/face_simple/training.py:158-251)
+  * the literal source lines of inference.py's loop   (inference.py:140-178, exec'd from the reference file)
+  * Trainer.train_step -> train_stage1                (training.py:138-156, 347-574: lip loss, post-fusion, face loss,
+                                                       loss.backward(), optimizer.step())
+The same callers run on the reference's own TalkingFace (PyTorch eager fp32 on the same GPU, TF32 off) for comparison.
+"""
+import copy
+import os
+import random
+import tempfile
+import textwrap
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import ref_shim
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def env():
+    import speech2lip_b200 as s2l
+    assert torch.cuda.is_available() and os.path.exists(s2l.LIB_PATH)
+    assert ref_shim.reference_available(), "the vendored reference (oracle/_ref, built by oracle/build_ref.py) is missing"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ns = ref_shim.load_reference()
+    import src.face_simple.config as fcfg
+    import src.face_simple.models as fmodels
+    import src.face_simple.models.tf_nerf as ftf
+    return types.SimpleNamespace(s2l=s2l, ns=ns, fcfg=fcfg, fmodels=fmodels, ftf=ftf, RefTalkingFace=ftf.TalkingFace)
+
+
+class patched:
+    """`with patched(env):` — the reference binds the drop-in wherever it would bind its own class."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def __enter__(self):
+        e = self.env
+        for mod in (e.fcfg, e.fmodels, e.ftf):
+            mod.TalkingFace = e.s2l.TalkingFace
+        return self
+
+    def __exit__(self, *a):
+        e = self.env
+        for mod in (e.fcfg, e.fmodels, e.ftf):
+            mod.TalkingFace = e.RefTalkingFace
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def make_cfg(env, face=500):
+    cfg = copy.deepcopy(env.ns.cfg)
+    # no LPIPS / SyncNet weights and no 3DMM pose files exist offline; everything else is may.yaml
+    cfg["training"].update(use_canonical_depth_loss_photo_v2=False, use_perceptual_loss=False, use_syncloss=False, multi_gpu=False,
+                           local_rank=0)
+    cfg["model"].update(canonical_depth_height=face, canonical_depth_width=face)
+    return cfg
+
+
+def build_pair(env, cfg, kind="kaiming"):
+    """(reference model, drop-in built by the reference's own factory with the class patched), identical state dicts."""
+    torch.manual_seed(7)
+    ref = env.fcfg.get_model(cfg, device=dev()).to(dev())
+    ref.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, kind, 2, 3).items()}, strict=False)
+    with patched(env):
+        drop = env.fcfg.get_model(cfg, device=dev()).to(dev())
+    assert type(drop) is env.s2l.TalkingFace and type(ref) is env.RefTalkingFace
+    res = drop.load_state_dict(ref.state_dict(), strict=True)      # every one of the 115 keys, shapes included
+    assert not res.missing_keys and not res.unexpected_keys
+    return ref, drop
+
+
+def make_data(H, W, h, w, seed=3, x0=None, y0=None):
+    g = torch.Generator().manual_seed(seed)
+    x0 = (w - W) // 2 if x0 is None else x0
+    y0 = (h - H) // 2 if y0 is None else y0
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+    coord = torch.stack([xs, ys], -1)[None] * 1.04 + 0.01 * torch.randn(1, h, w, 2, generator=g)
+    data = dict(rgb=torch.rand(1, H, W, 3, generator=g), rgb_zero=torch.rand(1, H, W, 3, generator=g),
+                audio=torch.randn(1, 16, 29, generator=g), index=torch.tensor([5]), total_frame=torch.tensor([100]),
+                coord=coord, rgb_face_zero=torch.rand(1, h, w, 3, generator=g), rgb_face_ori=torch.rand(1, h, w, 3, generator=g),
+                mask_lip_canonical=torch.zeros(1, h, w, 3), lip_lefttop_x=torch.tensor([x0]), lip_lefttop_y=torch.tensor([y0]))
+    data["mask_lip_canonical"][:, y0 + 1:y0 + H - 1, x0 + 1:x0 + W - 1] = 1
+    return data
+
+
+def test_real_predict_lip_image_drives_the_dropin(env):
+    """Trainer.predict_lip_image itself (its tiling, its eps_shift draw, its four rgb_forward calls, its blend), model
+    swapped: inference (no_grad: constant-latent rows -> tensor-core kernel) and training mode (autograd.Function)."""
+    H, W = 80, 120
+    cfg = make_cfg(env)
+    ref, drop = build_pair(env, cfg)
+    out = {}
+    for name, m in (("ref", ref), ("drop", drop)):
+        tr = env.ns.Trainer(m, None, dev(), "/tmp", cfg=cfg, batch_rays=H * W, use_audio_net=True, use_time=True, use_audio=True,
+                            use_perceptual_loss=False, use_syncloss=False, multi_gpu=False)
+        tr.height, tr.width = H, W
+        coords = env.ns.get_coords(W, H, dev())
+        audio = torch.from_numpy(synth.make_audio(1, seed=5)).to(dev())
+        data = {"index": torch.tensor([9], device=dev())}
+        m.eval()
+        torch.manual_seed(11)
+        with torch.no_grad():
+            out[name, "eval"] = tr.predict_lip_image(0, coords, audio, None, data, None, None, None)
+        m.train()
+        torch.manual_seed(11)
+        rgb = tr.predict_lip_image(0, coords, audio, None, data, None, None, None)
+        assert rgb.requires_grad
+        rgb.square().mean().backward()
+        out[name, "train"] = rgb.detach()
+        out[name, "grad"] = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    e_eval = (out["ref", "eval"] - out["drop", "eval"]).abs().max().item()
+    e_train = (out["ref", "train"] - out["drop", "train"]).abs().max().item()
+    print("real predict_lip_image: eval %.2e (tensor-core constant-latent path), train %.2e (exact fp32 path)" % (e_eval, e_train))
+    assert e_eval < TOL and e_train < 3e-4
+    assert set(out["ref", "grad"]) == set(out["drop", "grad"])
+    worst = max(((out["ref", "grad"][k] - g).norm() / (out["ref", "grad"][k].norm() + 1e-12)).item() for k, g in out["drop", "grad"].items())
+    print("real predict_lip_image: worst relative gradient error over %d tensors %.2e" % (len(out["drop", "grad"]), worst))
+    assert worst < 1e-3
+
+
+def inference_loop_source():
+    """The loop of inference.py (the `for data, index in tqdm(test_loader):` block, inference.py:139-178), as text."""
+    lines = open(os.path.join(ref_shim.REF_ROOT, "inference.py")).read().splitlines()
+    start = next(i for i, l in enumerate(lines) if "for data, index in tqdm(test_loader):" in l)
+    end = next(i for i, l in enumerate(lines) if l.startswith("if __name__"))
+    return textwrap.dedent("\n".join(lines[start:end]))
+
+
+def test_real_inference_loop_source_runs_on_the_dropin(env):
+    """exec the reference's OWN loop lines (read from its inference.py, not restated) with `model` = reference / drop-in:
+    tiling, audio_merge_forward, cat, rgb_forward, post_fusion2_onlylip, cvtColor, imwrite — then compare the lip maps,
+    the fused faces and the JPEG files they wrote."""
+    import cv2
+    src = inference_loop_source()
+    assert "model.rgb_forward(" in src and "model.audio_merge_forward(audio)" in src and "cv2.imwrite" in src
+    H, W, face = 80, 120, 500
+    cfg = make_cfg(env, face)
+    ref, drop = build_pair(env, cfg)
+    ref.eval(), drop.eval()
+    frames = []
+    for i in range(3):
+        d = make_data(H, W, face, face, seed=20 + i)
+        d = {k: v for k, v in d.items() if k not in ("rgb", "total_frame")}
+        d["index"] = torch.tensor([40 + i])
+        frames.append((d, torch.tensor([i])))
+    got = {}
+    for name, m in (("ref", ref), ("drop", drop)):
+        outdir = tempfile.mkdtemp()
+        scope = dict(torch=torch, cv2=cv2, tqdm=lambda x: x, model=m, device=dev(), batch_size=H * W, width=W, height=H,
+                     get_coords=env.ns.get_coords, audio_dims=m.audio_dims, seed=0, use_post_fusion=True,
+                     args=types.SimpleNamespace(change_pose=-1), test_output_post_dir=outdir)
+        res = []
+        for d, idx in frames:
+            scope["test_loader"] = [({k: v.clone() for k, v in d.items()}, idx)]
+            exec(src, scope)
+            res.append((scope["rgb_img"].copy(), scope["rgb_face_recon"].copy(),
+                        cv2.imread(os.path.join(outdir, "%05d.jpg" % (int(idx) + 1))).astype(np.int32)))
+        got[name] = res
+    for (a_lip, a_face, a_jpg), (b_lip, b_face, b_jpg) in zip(got["ref"], got["drop"]):
+        e_lip, e_face = np.abs(a_lip - b_lip).max(), np.abs(a_face - b_face).max()
+        print("real inference loop: lip %.2e face (after UNet) %.2e jpeg max level diff %d" % (e_lip, e_face, np.abs(a_jpg - b_jpg).max()))
+        assert e_lip < TOL
+        assert e_face < 5e-3                      # 1e-3 on the lip crop through an untrained (random-init) UNet
+        assert np.abs(a_jpg - b_jpg).max() <= 4   # 8-bit levels after JPEG quantisation
+
+
+def test_real_train_step_runs_on_the_dropin(env):
+    """Trainer.train_step -> train_stage1 (training.py:347-574) unmodified, reference's own get_trainer factory, SGD:
+    lip photometric loss, post_fusion2_onlylip with the black-hole augmentation draw, face photometric loss,
+    loss.backward(), optimizer.step().  Same RNG seeds on both models -> same eps_shift / augmentation decisions; the
+    loss and every parameter update must agree (the update of an SGD step is lr * gradient)."""
+    H, W, face = 80, 120, 500
+    cfg = make_cfg(env, face)
+    ref, drop = build_pair(env, cfg)
+    lr = 1e-2
+    out = {}
+    for name, m in (("ref", ref), ("drop", drop)):
+        before = {k: v.detach().clone() for k, v in m.named_parameters()}
+        opt = torch.optim.SGD(m.parameters(), lr=lr)
+        if name == "drop":
+            with patched(env):
+                tr = env.fcfg.get_trainer(m, opt, cfg, dev())
+        else:
+            tr = env.fcfg.get_trainer(m, opt, cfg, dev())
+        losses = []
+        for step, aug_seed in enumerate((0, 1, 2)):          # random.random() > 0.5 picks the augmentation branch for some seeds
+            data = {k: v.to(dev()) for k, v in make_data(H, W, face, face, seed=30 + step).items()}
+            random.seed(aug_seed)
+            torch.manual_seed(100 + step)
+            loss, _ = tr.train_step(data, it=10)
+            losses.append(loss)
+        out[name] = (losses, {k: (before[k] - v.detach()) / lr for k, v in m.named_parameters()})
+    for a, b in zip(out["ref"][0], out["drop"][0]):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(a)), (out["ref"][0], out["drop"][0])
+    upd_r, upd_d = out["ref"][1], out["drop"][1]
+    moved = [k for k in upd_r if upd_r[k].abs().max() > 0]
+    assert any(k.startswith("pts_linears") for k in moved) and any(k.startswith("encoder_conv") for k in moved) \
+        and any(k.startswith("post_fusion_unet") for k in moved)
+    worst = max(((upd_r[k] - upd_d[k]).norm() / (upd_r[k].norm() + 1e-12)).item() for k in moved)
+    print("real train_step x3: losses %s vs %s; worst relative update error over %d tensors %.2e" % (out["ref"][0], out["drop"][0], len(moved), worst))
+    assert worst < 2e-3
