@@ -188,29 +188,34 @@ def test_real_train_step_runs_on_the_dropin(env):
     cfg = make_cfg(env, face)
     ref, drop = build_pair(env, cfg)
     lr = 1e-2
+    init = {k: v.detach().clone() for k, v in ref.state_dict().items()}
     out = {}
     for name, m in (("ref", ref), ("drop", drop)):
-        before = {k: v.detach().clone() for k, v in m.named_parameters()}
         opt = torch.optim.SGD(m.parameters(), lr=lr)
         if name == "drop":
             with patched(env):
                 tr = env.fcfg.get_trainer(m, opt, cfg, dev())
         else:
             tr = env.fcfg.get_trainer(m, opt, cfg, dev())
-        losses = []
-        for step, aug_seed in enumerate((0, 1, 2)):          # random.random() > 0.5 picks the augmentation branch for some seeds
+        steps = []
+        for step, aug_seed in enumerate((0, 1, 2, 3)):       # random.random() > 0.5 picks the augmentation branch for some seeds
+            m.load_state_dict(init)                          # every step starts from the same weights: steps are compared one by one
+            before = {k: v.detach().clone() for k, v in m.named_parameters()}
             data = {k: v.to(dev()) for k, v in make_data(H, W, face, face, seed=30 + step).items()}
+            random.seed(aug_seed)
+            aug = random.random() > 0.5
             random.seed(aug_seed)
             torch.manual_seed(100 + step)
             loss, _ = tr.train_step(data, it=10)
-            losses.append(loss)
-        out[name] = (losses, {k: (before[k] - v.detach()) / lr for k, v in m.named_parameters()})
-    for a, b in zip(out["ref"][0], out["drop"][0]):
-        assert abs(a - b) < 2e-4 * max(1.0, abs(a)), (out["ref"][0], out["drop"][0])
-    upd_r, upd_d = out["ref"][1], out["drop"][1]
-    moved = [k for k in upd_r if upd_r[k].abs().max() > 0]
-    assert any(k.startswith("pts_linears") for k in moved) and any(k.startswith("encoder_conv") for k in moved) \
-        and any(k.startswith("post_fusion_unet") for k in moved)
-    worst = max(((upd_r[k] - upd_d[k]).norm() / (upd_r[k].norm() + 1e-12)).item() for k in moved)
-    print("real train_step x3: losses %s vs %s; worst relative update error over %d tensors %.2e" % (out["ref"][0], out["drop"][0], len(moved), worst))
-    assert worst < 2e-3
+            steps.append((loss, aug, {k: (before[k] - v.detach()) / lr for k, v in m.named_parameters()}))
+        out[name] = steps
+    assert {a for _, a, _ in out["ref"]} == {True, False}, "both post-fusion branches must be exercised"
+    for (la, aug, ua), (lb, _, ub) in zip(out["ref"], out["drop"]):
+        assert abs(la - lb) < 1e-4 * max(1.0, abs(la)), (la, lb)
+        moved = [k for k in ua if ua[k].abs().max() > 0]
+        assert any(k.startswith("pts_linears") for k in moved) and any(k.startswith("encoder_conv") for k in moved) \
+            and any(k.startswith("post_fusion_unet") for k in moved)
+        worst = max(((ua[k] - ub[k]).norm() / (ua[k].norm() + 1e-12)).item() for k in moved)
+        print("real train_step (black-hole augmentation %s): loss %.6f vs %.6f; worst relative update error over %d tensors %.2e"
+              % (aug, la, lb, len(moved), worst))
+        assert worst < 2e-3
