@@ -161,6 +161,27 @@ int32_t s2l_rgb_forward_rows_train(const void* blob, const float* x, int64_t n_r
 int32_t s2l_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts, int64_t n_rows, float* dsave,
                          int32_t out_ch, void* stream);
 
+/* ---- Training render on tensor cores (bf16 operands, fp32 accumulate) -------------------------------------------------
+ * Replaces: autograd through Trainer.predict_lip_image -> TalkingFace.rgb_forward for F frames x 4 taps
+ * (training.py:158-251, loss.backward() training.py:559; the five-frame sync-expert window training.py:500-548 is the same
+ * call with F = 5) as ONE differentiable launch sequence instead of 4 F rgb_forward calls:
+ *   s2l_train_fwd : latent [F,64] (AudioNet's output, tf_nerf.py:197-213) + frame_idx [F] -> frame_bias [F,4,256], then the
+ *                   fused bf16 MLP with the 4-tap blend in its epilogue -> rgb [F,H,W,3]; saves h0..h7 and the positional
+ *                   encodings (bf16) in `workspace` for the backward.
+ *   s2l_train_bwd : d_rgb [F,H,W,3] -> gradients of every MLP tensor in the reference's layouts, written (not accumulated)
+ *                   to grads_host[S2L_P_FC_UV_W .. S2L_NUM_PARAMS-1] (HOST array of DEVICE pointers in S2L_P_* order, fp32;
+ *                   entries of the AudioNet tensors are ignored), and d_latent [F,64] for AudioNet's own backward.
+ *                   Kernels: tensor-core data-gradient chain (tcgen05, dPre kept in TMEM between layers), split-K
+ *                   tensor-core weight-gradient GEMMs on MN-major operands, slab reduction + chain rule through the folded
+ *                   input layers.  No library GEMM is called.
+ * geom: pts_mode = S2L_PTS_GRID_ENS4, uv_dims = 2, out_ch = 3, eps_shift / eps_per_frame as for s2l_render_frames.
+ * workspace must hold s2l_train_workspace_bytes(geom) bytes and stay untouched between fwd and bwd (~9.3 KB per point). */
+size_t  s2l_train_workspace_bytes(const S2LGeom* geom);
+int32_t s2l_train_fwd(const void* blob, const S2LGeom* geom, const float* latent, const int64_t* frame_idx, float* rgb,
+                      float* frame_bias, void* workspace, void* stream);
+int32_t s2l_train_bwd(const void* blob, const S2LGeom* geom, const float* d_rgb, const float* latent, const int64_t* frame_idx,
+                      const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream);
+
 /* Replaces: Embedder.__call__ (tf_nerf.py:404-425): x rows (first uv_dims floats of each row_stride-float row) -> pe [N,E]. */
 int32_t s2l_embed_fwd(const float* x, int64_t n_rows, int32_t row_stride, int32_t uv_dims, float* pe, void* stream);
 

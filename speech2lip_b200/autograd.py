@@ -127,3 +127,66 @@ def rgb_forward_train(module, x, time_idx):
         div = torch.exp(torch.arange(0, 20, 2, dtype=torch.float) * -(math.log(10000.0) / 20)).to(x.device)   # tf_nerf.py:431-432
         module.__dict__["_div_term"] = div
     return FusedMLPRows.apply(x, time_idx, module.packed_weights(), div, *params)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Tensor-core training render: F frames x 4 taps in ONE differentiable launch sequence (include/speech2lip_b200.h,
+# s2l_train_fwd / s2l_train_bwd).  Replaces autograd through Trainer.predict_lip_image (training.py:158-251) called once
+# per frame — and five more times per frame for the sync-expert window (training.py:500-548).  bf16 operands, fp32 accumulate.
+MLP_PARAM_NAMES = _cabi.PARAM_NAMES[12:]          # fc_uv ... output_linear, S2L_P_* order
+
+
+class FusedLipRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, latent, index, eps, H, W, packed, *params):
+        lib = _cabi.lib()
+        if packed.uv_dims != 2 or packed.out_ch != 3:
+            raise ValueError("the training render is the live 4-tap mode (uv_dims=2, output_ch=3)")
+        latent = latent.contiguous().float()
+        F = latent.shape[0]
+        dev = latent.device
+        idx = torch.as_tensor(index).to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        eps = torch.as_tensor(eps, dtype=torch.float32).to(dev).reshape(-1)
+        eps = (eps.expand(F) if eps.numel() == 1 else eps).contiguous()
+        if idx.numel() != F or eps.numel() != F:
+            raise ValueError("index / eps_shift must have one entry per frame")
+        g = _cabi.S2LGeom(n_frames=F, height=int(H), width=int(W), n_samples=0, pts_mode=_cabi.PTS_GRID_ENS4, uv_dims=2, out_ch=3,
+                          z_per_ray=0, rays_per_frame_shared=0, pts_per_frame=0, eps_shift=0.0, eps_per_frame=eps.data_ptr())
+        ws = torch.empty(lib.s2l_train_workspace_bytes(C.byref(g)), dtype=torch.uint8, device=dev)
+        rgb = torch.empty(F, H, W, 3, device=dev)
+        bias = torch.empty(F, 4, 256, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.s2l_train_fwd(_ptr(packed.blob), C.byref(g), _ptr(latent), _ptr(idx), _ptr(rgb), _ptr(bias), _ptr(ws),
+                                          _stream()), "s2l_train_fwd")
+        ctx.packed, ctx.geom = packed, g
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(latent, idx, eps, bias, ws)
+        return rgb
+
+    @staticmethod
+    def backward(ctx, d_rgb):
+        lib = _cabi.lib()
+        latent, idx, eps, bias, ws = ctx.saved_tensors
+        dev = latent.device
+        d_rgb = d_rgb.contiguous().float()
+        grads = [torch.empty(sh, device=dev) for sh in ctx.shapes]
+        d_latent = torch.empty_like(latent)
+        arr = (C.c_void_p * _cabi.NUM_PARAMS)(*([None] * 12 + [g.data_ptr() for g in grads]))
+        with torch.cuda.device(dev):
+            _cabi.check(lib.s2l_train_bwd(_ptr(ctx.packed.blob), C.byref(ctx.geom), _ptr(d_rgb), _ptr(latent), _ptr(idx), _ptr(bias),
+                                          _ptr(ws), arr, _ptr(d_latent), _stream()), "s2l_train_bwd")
+        return (d_latent, None, None, None, None, None, *grads)
+
+
+def render_lip_train(module, audio, index, H, W, eps_shift=None):
+    """Differentiable 4-tap render of F lip frames (speech2lip_b200.TalkingFace.render_lip_train).  audio [F,16,29] (or
+    [F,29,16]), index [F]; eps_shift: [F] / scalar, or None to draw one per frame exactly as predict_lip_image does
+    (training.py:198-200: ry * torch.rand(1, device) / 2 per call, frames in order)."""
+    dev = audio.device
+    F = audio.shape[0]
+    if eps_shift is None:
+        eps_shift = torch.cat([(0.5 / H) * torch.rand(1, device=dev) / 2.0 for _ in range(F)])
+    latent = module.audio_merge_forward(audio)                      # AudioNet on autograd (67 k MAC per frame)
+    sd = module._hot_params()
+    params = [sd[n] for n in MLP_PARAM_NAMES]
+    return FusedLipRender.apply(latent, index, eps_shift, int(H), int(W), module.packed_weights(), *params)

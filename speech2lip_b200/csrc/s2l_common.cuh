@@ -93,8 +93,18 @@ constexpr int D_TOTAL = D_SLOTS * 65536;
 constexpr int kScaleA = 8;      // activation residual (A - fp16(A)) is scaled by 2^+8 before e4m3; W1 copy by 2^-8
 constexpr int kScaleW = 10;     // weight residual (W - fp16(W)) is scaled by 2^+10 before e4m3; A1 copy by 2^-10
 
+// ---- TCWT section: bf16 B operands of the tensor-core BACKWARD data-gradient GEMMs dH_{l-1} = dPre_l * W_l
+//      (s2l_train_dgrad.cu): granules [128 N-rows = input channels x 64 K = output channels] of W^T, hi plane only
+//      (16 KB, same K-major SW128 image as TCW), in issue order: output_linear^T (2 granules, K = out_ch padded to 64),
+//      then pts_linears 7, 6, 5[:, 256:], 4, 3, 2, 1 (8 granules each: half h, K-chunk kc).
+constexpr int kTGran = kGranPlane;                        // 16 KB
+constexpr int kTLayers = 7;
+constexpr int kTcwtBytes = (2 + kTLayers * 8) * kTGran;   // 950 272 B
+__host__ __device__ constexpr int t_layer_src(int i) { return 7 - i; }            // i-th dgrad layer reads pts_linears[7 - i]
+__host__ __device__ constexpr int t_layer_off(int i) { return (2 + i * 8) * kTGran; }
+
 struct Layout {
-  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, off_tcw8, total;
+  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, off_tcw8, off_tcwt, total;
 };
 __host__ __device__ inline Layout blob_layout() {
   Layout L;
@@ -107,6 +117,7 @@ __host__ __device__ inline Layout blob_layout() {
   L.off_tcw = o;    o = al(o + kTcwBytes);
   L.off_dgrad = o;  o = al(o + sizeof(float) * D_TOTAL);
   L.off_tcw8 = o;   o = al(o + kTcwBytes);
+  L.off_tcwt = o;   o = al(o + kTcwtBytes);
   L.total = o;
   return L;
 }

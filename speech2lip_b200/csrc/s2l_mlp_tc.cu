@@ -58,7 +58,9 @@ static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
 // fetches half of every granule and multicasts it into both CTAs' rings, halving the L2 reads / crossbar traffic per
 // weight byte delivered (worth ~+3 % sustained); MMAs, TMEM and epilogues stay per CTA,
 // the only coupling is the ring (a stage is refilled when BOTH CTAs released it).
-template <int NPASS, int UVD, int CL>
+// TRAIN (bf16 single pass only): additionally saves h0..h7 and the positional encodings for the backward kernels
+// (s2l_train_dgrad.cu, s2l_train_wgrad.cu).
+template <int NPASS, int UVD, int CL, bool TRAIN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T1_SM_BAR);
@@ -351,7 +353,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
       const long long p = p0 + r;
       mbar_wait_wd<true>(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
-      pe_write_row<NPASS, UVD>(a.src, f, p, p < Pf, r, smem + SM_PE + buf * PE_BUF);
+      pe_write_row<NPASS, UVD>(a.src, f, p, p < Pf, r, smem + SM_PE + buf * PE_BUF,
+                               (TRAIN && tile < n_tiles) ? reinterpret_cast<uint4*>(a.save_pe + ((size_t)tile * TC_TM + r) * 64) : nullptr);
       {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
         float* dst = fbias_s + buf * 512;
@@ -406,6 +409,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             else convert_slice<NPASS>(va, b4, o);
             if (NPASS != 1) tmem_st32(taddr, o);
             else tmem_st16(taddr, o);
+            if (TRAIN && tile < n_tiles) {     // h_g as the next layer consumes it: 32 bf16 = 64 B of this row
+              uint4* dst = reinterpret_cast<uint4*>(a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+            }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&epi_done[q]);
@@ -461,14 +469,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   }
 }
 
-template <int NPASS, int UVD, int CL>
+template <int NPASS, int UVD, int CL, bool TRAIN = false>
 static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
-    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mlp_tc_kernel<NPASS, UVD, CL, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM_BYTES) != cudaSuccess) {
       set_error("mlp_tc: cannot opt in to %d B of shared memory: %s", T1_SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
       return 6;
     }
@@ -490,8 +498,8 @@ static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   at.val.clusterDim.z = 1;
   cfg.attrs = &at;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, mlp_tc_kernel<NPASS, UVD, CL>, a);
-  return check_launch("mlp_tc_kernel") ? 0 : 5;
+  cudaLaunchKernelEx(&cfg, mlp_tc_kernel<NPASS, UVD, CL, TRAIN>, a);
+  return check_launch(TRAIN ? "mlp_tc_kernel<train>" : "mlp_tc_kernel") ? 0 : 5;
 }
 
 template <int CL>
@@ -581,6 +589,29 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
   }
   if (impl == 3) return launch_tc_cl<2>(a, n_tiles, npass, src.uv_dims, st);
   return launch_tc_cl<1>(a, n_tiles, npass, src.uv_dims, st);
+}
+
+// Training forward (s2l_train_fwd): the live 4-tap render of F frames in bf16 with the fused blend epilogue, saving the
+// activations the backward needs.  Always the single-CTA schedule (training launches are a few thousand tiles).
+int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* rgb,
+                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st) {
+  TcArgs a{};
+  a.blob = reinterpret_cast<const uint8_t*>(blob);
+  a.L = blob_layout();
+  a.src = src;
+  a.frame_bias = frame_bias;
+  a.out_ch = 3;
+  a.n_frames = n_frames;
+  a.tiles_per_frame = (src.P + TC_TM - 1) / TC_TM;
+  a.epi_mode = EPI_ENS4;
+  a.rgb = rgb;
+  a.save_h = save_h;
+  a.save_pe = save_pe;
+  const long long n_tiles = a.tiles_per_frame * n_frames;
+  a.rows_total = n_tiles * TC_TM;
+  if (n_tiles == 0) return 0;
+  if (src.mode != S2L_PTS_GRID_ENS4 || src.uv_dims != 2) { set_error("mlp_tc_train: the training render is the 4-tap live mode (uv_dims = 2)"); return 2; }
+  return launch_tc_impl<1, 2, 1, true>(a, n_tiles, st);
 }
 
 }  // namespace s2l

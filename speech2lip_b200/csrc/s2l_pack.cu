@@ -168,6 +168,29 @@ __global__ void pack_tcw_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch
   base8[plane + plane / 2 + off8] = (uint8_t)__nv_cvt_float_to_fp8(w2f * (float)(1 << kScaleW), __NV_SATFINITE, __NV_E4M3);
 }
 
+// ---- TCWT: transposed bf16 granules for the backward data-gradient GEMMs (see s2l_common.cuh)
+__global__ void pack_tcwt_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per element
+  const long long per_gran = 128 * 64;
+  if (gid >= (long long)(2 + kTLayers * 8) * per_gran) return;
+  const int gran = (int)(gid / per_gran);
+  const int r = (int)(gid % per_gran);
+  const int n = r / 64, k = r % 64;
+  float v;
+  if (gran < 2) {                       // output_linear^T: row = hidden channel, k = output channel
+    const int ni = gran * 128 + n;
+    v = (k < out_ch) ? P.p[S2L_P_OUT_W][k * 256 + ni] : 0.f;
+  } else {
+    const int i = (gran - 2) / 8, gi = (gran - 2) % 8;
+    const int h = gi / 4, kc = gi % 4;
+    const int l = t_layer_src(i);
+    const int ni = h * 128 + n, ko = kc * 64 + k;
+    v = (l == 5) ? pts_w(P, 5)[ko * 512 + 256 + ni] : pts_w(P, l)[ko * 256 + ni];
+  }
+  uint8_t* base = blob + L.off_tcwt + (size_t)gran * kTGran;
+  *reinterpret_cast<__nv_bfloat16*>(base + sw128_off(n, k)) = __float2bfloat16_rn(v);
+}
+
 }  // namespace s2l
 
 using namespace s2l;
@@ -210,5 +233,8 @@ extern "C" int32_t s2l_pack_weights(const float* const* params_host, void* blob,
   const long long n_elem = (long long)kTcwBytes / 4;   // one thread per (hi,lo) element pair
   pack_tcw_kernel<<<(unsigned)((n_elem + 255) / 256), 256, 0, st>>>(P, b, L, out_ch);
   if (!check_launch("pack_tcw_kernel")) return 5;
+  const long long n_t = (long long)(2 + kTLayers * 8) * 128 * 64;
+  pack_tcwt_kernel<<<(unsigned)((n_t + 255) / 256), 256, 0, st>>>(P, b, L, out_ch);
+  if (!check_launch("pack_tcwt_kernel")) return 5;
   return 0;
 }

@@ -45,6 +45,11 @@ struct TcArgs {
                              //     whose last-sample density is too close to zero to trust the tensor-core sign
   float term_thr;            // non-final chunk: a ray whose transmittance fell below term_thr is finished
   float fix_thr;             // final chunk: |sigma_last| < fix_thr -> listed for the fp32 re-evaluation (0: never)
+  // ---- training forward (TRAIN instantiation, bf16): what the backward kernels need, tile-major rows (row = tile * 128 + r,
+  //      rows of a tile past the frame's last point hold finite garbage that the backward multiplies by zero gradients)
+  __nv_bfloat16* save_h;     // [8][rows_total][256] post-ReLU activations h0..h7 exactly as the next layer's MMA consumed them
+  __nv_bfloat16* save_pe;    // [rows_total][64] positional encodings (bf16), the B operand of the fold weight gradients
+  long long rows_total;      // n_tiles * 128
 };
 
 
@@ -333,7 +338,8 @@ __device__ __forceinline__ void convert_slice(const uint32_t (&v)[32], const flo
 // to 64) written as row r of the K-major A-operand image(s) of a 128-row tile: bf16 hi (+ lo) SW128 planes, or for
 // NPASS == 2 the fp16 SW128 plane + e5m2 / e4m3 SW64 planes.  `valid` = the point exists (rows past the end are zeros).
 template <int NPASS, int UVD>
-__device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long long p, bool valid, int r, uint8_t* hi_base) {
+__device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long long p, bool valid, int r, uint8_t* hi_base,
+                                             uint4* gsave = nullptr) {
   float e[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) e[i] = 0.f;
@@ -406,6 +412,7 @@ __device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long lo
     const int off = row_off + ((j ^ (r & 7)) << 4);
     *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
     if (NPASS == 3) *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    if (gsave) gsave[j] = make_uint4(h[0], h[1], h[2], h[3]);          // training forward: the row in natural order
   }
   }
 }

@@ -243,6 +243,14 @@ class TalkingFace(nn.Module):
             return R.rgb_forward_const_latent(self.packed_weights(), x, t, self.dropin_precision)
         return R.rgb_forward_rows(self.packed_weights(), uv_audio_pts, t)
 
+    def render_lip_train(self, audio, index, H, W, eps_shift=None):
+        """F lip frames through the 4-tap local ensemble in ONE differentiable launch sequence on tensor cores (bf16):
+        what Trainer.predict_lip_image (training.py:158-251) computes per frame, for a batch of frames / the five-frame
+        sync-expert window (training.py:500-548).  Gradients reach every hot-path parameter including AudioNet.
+        audio [F,16,29], index [F] (time_pts of each frame) -> rgb [F,H,W,3]."""
+        from .autograd import render_lip_train
+        return render_lip_train(self, audio, index, H, W, eps_shift)
+
     def renderer(self, precision="bf16x3"):
         """Batched frame renderer (not expressible through the reference's per-call contract)."""
         return R.LipRenderer(self.packed_weights(), precision)
