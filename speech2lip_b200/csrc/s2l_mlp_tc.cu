@@ -48,7 +48,7 @@ constexpr int T1_STAGE = kGranBytes;                // 32 KB: both planes of a g
 constexpr int T1_SM_TCBIAS = SM_STG + T1_NSTG * T1_STAGE;
 constexpr int T1_SM_FBIAS = T1_SM_TCBIAS + kNumG * 256 * 4;
 constexpr int T1_SM_BAR = T1_SM_FBIAS + 2 * 2 * 256 * 4;
-constexpr int T1_NBAR = 2 * T1_NSTG + 2 + 2 + 4 + 4 + 2 + 2;
+constexpr int T1_NBAR = 2 * T1_NSTG + 2 + 2 + 4 + 4 + 2 + 2 + 2;
 constexpr int T1_SM_TMEMPTR = T1_SM_BAR + T1_NBAR * 8;
 constexpr int T1_SM_RAW = T1_SM_TMEMPTR + 16;          // 2 x [128] float4: output tile handed to the reducer warp
 constexpr int T1_SMEM_BYTES = T1_SM_RAW + 2 * TC_TM * 16;
@@ -72,6 +72,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   uint64_t* epi_done = acc_full + 4;
   uint64_t* raw_full = epi_done + 4;
   uint64_t* raw_empty = raw_full + 2;
+  // The output layer has its own accumulator-ready barrier.  On acc_full[0] its completion would be followed by the NEXT
+  // tile's G0 completion with nothing in between that depends on the epilogue; an epilogue warp whose barrier poll is
+  // delayed past both (its polls queue behind global stores in the training forward) would see the 1-bit phase flip twice
+  // and wait forever.
+  uint64_t* acc_out = raw_empty + 2;
   float4* rawbuf = reinterpret_cast<float4*>(smem + T1_SM_RAW);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + T1_SM_TMEMPTR);
   float* tcbias_s = reinterpret_cast<float*>(smem + T1_SM_TCBIAS);
@@ -111,6 +116,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       mbar_init(&acc_full[q], 1);
       mbar_init(&epi_done[q], 256);
     }
+    mbar_init(acc_out, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       wait_quarter(0); granule(S2L_IC(0), S2L_BC(false), S2L_BC(true), d_region, a_region, 0u, nullptr, nullptr);
       wait_quarter(1); granule(S2L_IC(1), S2L_BC(false), S2L_BC(true), d_region, a_region + 64u, 1u, nullptr, nullptr);
       wait_quarter(2); granule(S2L_IC(2), S2L_BC(false), S2L_BC(true), d_region, a_region + 128u, 1u, nullptr, nullptr);
-      wait_quarter(3); granule(S2L_IC(3), S2L_BC(false), S2L_BC(true), d_region, a_region + 192u, 1u, &acc_full[0], nullptr);
+      wait_quarter(3); granule(S2L_IC(3), S2L_BC(false), S2L_BC(true), d_region, a_region + 192u, 1u, acc_out, nullptr);
       TL(0, 5080); TLC_FLUSH(0);
     }
 #undef S2L_IC
@@ -354,7 +360,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       const long long p = p0 + r;
       mbar_wait_wd<true>(&pe_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
       pe_write_row<NPASS, UVD>(a.src, f, p, p < Pf, r, smem + SM_PE + buf * PE_BUF,
+#ifndef S2L_DBG_NOSAVEPE
                                (TRAIN && tile < n_tiles) ? reinterpret_cast<uint4*>(a.save_pe + ((size_t)tile * TC_TM + r) * 64) : nullptr);
+#else
+                               nullptr);
+#endif
       {
         const float* fb = a.frame_bias + (size_t)f * 4 * 256 + 512;    // rows 2,3: folded bias0', bias5'
         float* dst = fbias_s + buf * 512;
@@ -409,11 +419,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             else convert_slice<NPASS>(va, b4, o);
             if (NPASS != 1) tmem_st32(taddr, o);
             else tmem_st16(taddr, o);
+#ifndef S2L_DBG_NOSAVEH
             if (TRAIN && tile < n_tiles) {     // h_g as the next layer consumes it: 32 bf16 = 64 B of this row
               uint4* dst = reinterpret_cast<uint4*>(a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32);
 #pragma unroll
               for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
             }
+#endif
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&epi_done[q]);
@@ -426,8 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       // ---- G8: raw output (no activation), tf_nerf.py:283
       {
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
-        mbar_wait_wd(&acc_full[0], acc_par[0], 800);
-        acc_par[0] ^= 1;
+        mbar_wait_wd(acc_out, (uint32_t)(it & 1), 800);
         tc_fence_after();
         if (half == 0) {
           uint32_t v[4];

@@ -32,7 +32,7 @@ constexpr int T2_SM_BAR = T2_SM_FBIAS + 2 * 2 * 256 * 4;
 // barrier map (64-bit slots): local b_empty[8] pe_full[2] pe_empty[2] acc_full[2] (slots 0-7 unused);
 // leader-side pair barriers pair_full[8] epi_done[4] pe_pair[2]
 constexpr int T2_BEMPTY = 8, T2_PEFULL = 16, T2_PEEMPTY = 18, T2_ACC = 20, T2_PAIRFULL = 22, T2_EPIDONE = 30,
-              T2_PEPAIR = 34, T2_RAWFULL = 36, T2_RAWEMPTY = 38, T2_NBAR = 40;
+              T2_PEPAIR = 34, T2_RAWFULL = 36, T2_RAWEMPTY = 38, T2_ACCOUT = 40, T2_NBAR = 42;
 constexpr int T2_SM_TMEMPTR = T2_SM_BAR + T2_NBAR * 8;
 constexpr int T2_SM_RAW = T2_SM_TMEMPTR + 16;          // 2 x [128] float4: output tile handed to the reducer warp
 constexpr int T2_SMEM_BYTES = T2_SM_RAW + 2 * TC_TM * 16;
@@ -113,6 +113,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
   uint64_t* pe_pair = bars + T2_PEPAIR;         // used in the leader only
   uint64_t* raw_full = bars + T2_RAWFULL;
   uint64_t* raw_empty = bars + T2_RAWEMPTY;
+  uint64_t* acc_out = bars + T2_ACCOUT;         // the output layer's own accumulator-ready barrier (see s2l_mlp_tc.cu)
   float4* rawbuf = reinterpret_cast<float4*>(smem + T2_SM_RAW);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + T2_SM_TMEMPTR);
   float* tcbias_s = reinterpret_cast<float*>(smem + T2_SM_TCBIAS);
@@ -140,6 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       mbar_init(&raw_empty[b], 1);
     }
     for (int q = 0; q < 4; ++q) mbar_init(&epi_done[q], 16);       // one arrive per epilogue warp of either CTA
+    mbar_init(acc_out, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -347,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
         wait_quarter(0); granule(S2L_IC(4), S2L_BC(false), S2L_BC(true), d_region, a_region, 0u, nullptr, nullptr);
         wait_quarter(1); granule(S2L_IC(5), S2L_BC(false), S2L_BC(true), d_region, a_region + 64u, 1u, nullptr, nullptr);
         wait_quarter(2); granule(S2L_IC(6), S2L_BC(false), S2L_BC(true), d_region, a_region + 128u, 1u, nullptr, nullptr);
-        wait_quarter(3); granule(S2L_IC(7), S2L_BC(false), S2L_BC(true), d_region, a_region + 192u, 1u, &acc_full[0], nullptr);
+        wait_quarter(3); granule(S2L_IC(7), S2L_BC(false), S2L_BC(true), d_region, a_region + 192u, 1u, acc_out, nullptr);
       }
 #undef S2L_IC
 #undef S2L_BC
@@ -433,8 +435,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_t
       // ---- G8: raw output (no activation), tf_nerf.py:283
       {
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
-        mbar_wait_wd(&acc_full[0], acc_par[0], 800);
-        acc_par[0] ^= 1;
+        mbar_wait_wd(acc_out, (uint32_t)(it & 1), 800);
         tc_fence_after();
         if (half == 0) {
           uint32_t v[4];

@@ -28,8 +28,8 @@ constexpr int DG_SM_DOUT = 0;                          // 2 x [128 rows][64 K] b
 constexpr int DG_SM_WOUT = DG_SM_DOUT + 2 * PE_PLANE;  // output_linear^T, 2 granules, resident
 constexpr int DG_SM_STG = DG_SM_WOUT + 2 * kTGran;
 constexpr int DG_SM_BAR = DG_SM_STG + DG_NSTG * DG_STAGE;
-// barriers: b_full[8] b_empty[8] wout_full do_full[2] do_empty[2] acc_full[2] epi_done[4]
-constexpr int DG_NBAR = 2 * DG_NSTG + 1 + 2 + 2 + 2 + 4;
+// barriers: b_full[8] b_empty[8] wout_full do_full[2] do_empty[2] acc_full[2] epi_done[4] acc_t8[2]
+constexpr int DG_NBAR = 2 * DG_NSTG + 1 + 2 + 2 + 2 + 4 + 2;
 constexpr int DG_SM_TMEMPTR = DG_SM_BAR + DG_NBAR * 8;
 constexpr int DG_SMEM_BYTES = DG_SM_TMEMPTR + 16;
 static_assert(DG_SMEM_BYTES <= 232448, "shared memory budget");
@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
   uint64_t* do_empty = do_full + 2;
   uint64_t* acc_full = do_empty + 2;
   uint64_t* epi_done = acc_full + 2;
+  // T8 has its own accumulator-ready barriers: it depends on nothing the epilogue produces, so the next tile's T8 (two
+  // MMAs) can complete while the epilogue is still inside the previous tile's last step — on a shared barrier two
+  // completions in a row would alias the 1-bit phase the epilogue is waiting for
+  uint64_t* acc_t8 = epi_done + 4;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + DG_SM_TMEMPTR);
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -84,6 +88,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
       mbar_init(&do_full[b], 128);
       mbar_init(&do_empty[b], 1);
       mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_t8[b], 1);
     }
     for (int q = 0; q < 4; ++q) mbar_init(&epi_done[q], 256);
     fence_barrier_init();
@@ -163,9 +168,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
         const uint32_t img = ((smem_u32(smem + DG_SM_DOUT + buf * PE_PLANE) >> 4) & 0x3FFFu) | 0x10000u;
         if (elect_one()) {
           umma_ss(d_region, mk(img), mk(wout0), idesc, 0u);
-          umma_commit(&acc_full[0]);
+          umma_commit(&acc_t8[0]);
           umma_ss(d_region + 128u, mk(img), mk(wout0 + (uint32_t)(kTGran >> 4)), idesc, 0u);
-          umma_commit(&acc_full[1]);
+          umma_commit(&acc_t8[1]);
           umma_commit(&do_empty[buf]);
         }
         __syncwarp();
@@ -213,9 +218,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
         const float w = __fdiv_rn(area[3 - tap], tot);
         const float* g = a.d_rgb + ((long long)f * npix + pix) * 3;
         d[0] = w * g[0]; d[1] = w * g[1]; d[2] = w * g[2];
-        sb0 += d[0]; sb1 += d[1]; sb2 += d[2];
       }
       const uint4 lo = make_uint4(cvt_bf16x2(d[0], d[1]), cvt_bf16x2(d[2], 0.f), 0u, 0u);
+      // the bias gradient sums the same bf16 values the weight-gradient GEMM multiplies
+      sb0 += __uint_as_float(lo.x << 16); sb1 += __uint_as_float(lo.x & 0xffff0000u); sb2 += __uint_as_float(lo.y << 16);
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
       uint4* g16 = reinterpret_cast<uint4*>(a.B.dout16 + ((size_t)tile * TC_TM + r) * 16);
       g16[0] = lo;
@@ -244,7 +250,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
     const int row = quad * 32 + lane;
     uint32_t acc_par[2] = {0, 0};
     int rp = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const size_t grow = (size_t)tile * TC_TM + row;
 #pragma unroll 1
       for (int step = 0; step < 8; ++step) {          // step s produces dPre_{7-s} from the accumulator of T8 / layer l = 8-s
@@ -261,8 +268,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
 #pragma unroll
             for (int t = 0; t < 4; ++t) hm[qq][t] = __ldg(src + t);
           }
-          mbar_wait_wd(&acc_full[hh], acc_par[hh], 700 + hh);
-          acc_par[hh] ^= 1;
+          if (step == 0) {
+            mbar_wait_wd(&acc_t8[hh], (uint32_t)(it & 1), 710 + hh);
+          } else {
+            mbar_wait_wd(&acc_full[hh], acc_par[hh], 700 + hh);
+            acc_par[hh] ^= 1;
+          }
           tc_fence_after();
           const uint32_t taddr0 = d_region + lane_sel + (uint32_t)(hh * 128 + half * 32);
 #pragma unroll
