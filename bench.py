@@ -167,6 +167,92 @@ def eager_gpu_reference(a, dev):
     return out
 
 
+def train_step_extras(dev, sizes=((80, 120), (256, 256)), frames=4, window=5, reps=3):
+    """BASELINE.json configs[4]: a 4-frame training batch, each frame with its 5-frame sync-expert window
+    (training.py:404-559: predict_lip_image for the frame, training.py:500-525: five more for the window), forward +
+    backward + optimizer step, bf16 on tensor cores — against the reference's own modules (PyTorch eager fp32 autograd,
+    TF32 off) doing the same renders through Trainer.predict_lip_image on the same GPU.  Timed: the lip-render part of the
+    step (AudioNet + 4-tap MLP renders + photometric loss + backward + SGD step); the UNet / SyncNet / LPIPS tail of a
+    real step is cuDNN code shared by both arms and is not included.  Wall clock, synchronised, per step."""
+    import speech2lip_b200 as s2l
+    from speech2lip_b200 import synth
+    out = {}
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    G = 1 + window                                    # renders per frame
+    for (H, W) in sizes:
+        key = "train_step_config5_%dx%d" % (H, W)
+        try:
+            sd = {k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming", 2, 3).items()}
+            gen = torch.Generator().manual_seed(5)
+            audio = torch.from_numpy(synth.make_audio(frames * G, seed=21)).to(dev)
+            index = torch.arange(frames * G)
+            target = torch.rand(frames * G, H, W, 3, generator=gen).to(dev)
+            m = s2l.TalkingFace(device=dev, cfg=cfg).to(dev).train()
+            m.load_state_dict(sd, strict=False)
+            opt = torch.optim.SGD([p for n, p in m.named_parameters() if not n.startswith(("post_fusion", "canonical", "coord_"))], lr=1e-5)
+
+            def ours_step(group):
+                """group = frames per launch: 1 -> one launch per frame (its 6 renders), `frames` -> the whole batch in one launch"""
+                for f0 in range(0, frames, group):
+                    sl = slice(f0 * G, (f0 + group) * G)
+                    opt.zero_grad(set_to_none=True)
+                    rgb = m.render_lip_train(audio[sl], index[sl], H, W)
+                    ((rgb - target[sl]) ** 2).mean().backward()
+                    opt.step()
+
+            def timeit(fn, n):
+                fn(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / n * 1e3
+            pts = frames * G * H * W * 4
+            ws_gb = pts * 9.3e3 / 1e9
+            rec = {"frames": frames, "renders_per_frame": G, "point_evals_per_step": pts, "precision": "bf16 (fp32 accumulate)",
+                   "ours_ms_per_frame_launches": timeit(lambda: ours_step(1), reps)}
+            if ws_gb < 60:
+                rec["ours_ms_one_launch"] = timeit(lambda: ours_step(frames), reps)
+            best = min(v for k, v in rec.items() if k.startswith("ours_ms"))
+            rec["ms_per_step"] = best
+            rec["frames_per_s"] = frames / (best * 1e-3)
+            rec["train_tflops_algorithmic"] = 3 * pts * FLOP_PER_POINT["ensemble4"] / (best * 1e-3) / 1e12
+            # ---- the reference's own modules, eager fp32 autograd
+            try:
+                from oracle import ref_runner as RR
+                if RR.available():
+                    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+                    torch.backends.cuda.matmul.allow_tf32 = False
+                    torch.backends.cudnn.allow_tf32 = False
+                    rm = RR.model(2, 3, dev, mode="train")
+                    tr = RR.trainer(rm, dev, H, W)
+                    ropt = torch.optim.SGD([p for n, p in rm.named_parameters() if not n.startswith(("post_fusion", "canonical", "coord_"))], lr=1e-5)
+                    coords = RR.ns().get_coords(W, H, dev)
+
+                    def ref_step():
+                        for f in range(frames):
+                            ropt.zero_grad(set_to_none=True)
+                            loss = 0
+                            for j in range(G):
+                                i = f * G + j
+                                rgb = tr.predict_lip_image(0, coords, audio[i:i + 1], None, {"index": index[i:i + 1].to(dev)}, None, None, None)
+                                loss = loss + ((rgb.view(H, W, 3) - target[i]) ** 2).mean() / G
+                            loss.backward()
+                            ropt.step()
+                    rec["reference_eager_ms"] = timeit(ref_step, 2)
+                    rec["speedup_vs_reference_eager"] = rec["reference_eager_ms"] / best
+                    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+                    del rm, tr, ropt
+            except Exception as e:
+                rec["reference_eager_error"] = str(e)[:200]
+            out[key] = rec
+            del m, opt
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[key] = {"error": str(e)[:300], "frames_per_s": 0.0, "ms_per_step": 0.0}
+    return out
+
+
 def run_reference_arm(a):
     """`--impl reference`: the reference's own CPU implementation of the path on all host cores; each step = ONE WHOLE
     frame of the workload (no extrapolation) unless --cpu-rays bounds it."""
@@ -447,6 +533,7 @@ def run_gpu_arm(a):
             extras.update(eager_gpu_reference(a, dev))
         except Exception as e:
             extras["reference_gpu_eager"] = {"error": str(e)[:200], "frames_per_s": 0.0, "ms_per_step": 0.0}
+        extras.update(train_step_extras(dev))
 
     t = torch.tensor([dev_ms, e2e_ms, ker_ms], device=dev, dtype=torch.float64)
     if world > 1:
