@@ -136,6 +136,22 @@ int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, int64_t laten
 int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
                         void* stream);
 
+/* The same two caller patterns WITHOUT a host synchronisation (what the drop-in TalkingFace calls): the compare kernel
+ * leaves its verdict in device memory and the kernels that follow are gated on it.
+ *   s2l_audio_merge_auto : audio [B,16,29] (transposed=1: [B,29,16]) -> latent [B,64]; encodes row 0, then either
+ *                          broadcasts it (all rows equal) or encodes every row.
+ *   s2l_rgb_forward_auto : x [N, uv_dims+64], time_idx_dev = DEVICE int64[1] (position[0], tf_nerf.py:439; NULL: no time
+ *                          term) -> out [N,out_ch].  Rows with one common latent run the fused tensor-core MLP in
+ *                          `precision` (S2L_PREC_BF16X3 / FP16F8 / BF16X1) reading the coordinates in place (row stride
+ *                          uv_dims+64); otherwise the general fp32 per-row kernel runs.  S2L_PREC_FP32: always the latter.
+ * scratch: s2l_*_auto_scratch_bytes() bytes of device memory per in-flight call. */
+size_t  s2l_audio_merge_auto_scratch_bytes(void);
+int32_t s2l_audio_merge_auto(const void* blob, const float* audio, int32_t transposed, int64_t n_rows, float* latent,
+                             void* scratch, void* stream);
+size_t  s2l_rgb_forward_auto_scratch_bytes(void);
+int32_t s2l_rgb_forward_auto(const void* blob, const float* x, int64_t n_rows, const int64_t* time_idx_dev, float* out,
+                             int32_t uv_dims, int32_t out_ch, int32_t precision, void* scratch, void* stream);
+
 /* Replaces: TalkingFace.rgb_forward (tf_nerf.py:225-285) for F frames x P points with a
  * per-frame-constant latent (frame_bias from s2l_audio_encode_fwd).  Point coordinates come from
  * geom->pts_mode.  raw_out [F*P_padless, out_ch] receives the raw linear outputs in point order. */

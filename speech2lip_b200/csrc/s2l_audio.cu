@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
                                                            const float* __restrict__ audio, int transposed,
                                                            const long long* __restrict__ frame_idx,
                                                            float* __restrict__ latent, float* __restrict__ frame_bias,
-                                                           const float* __restrict__ latent_in, long long latent_in_stride) {
+                                                           const float* __restrict__ latent_in, long long latent_in_stride,
+                                                           int n_frames, const int* __restrict__ gate_flag,
+                                                           const float* __restrict__ lat0) {
   const float* A = reinterpret_cast<const float*>(blob + L.off_audio);
   const float* C = reinterpret_cast<const float*>(blob + L.off_const);
   const float* Fp = reinterpret_cast<const float*>(blob + L.off_fp32);
@@ -43,8 +45,15 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
   __shared__ float x1[32 * 8], x2[32 * 4], x3[64 * 2], x4[64], x5[64], lat[64];
   __shared__ float pe[kTimePE];
   __shared__ float b0s[256], bss[256];
-  const int f = blockIdx.x, tid = threadIdx.x;
-
+  const int tid = threadIdx.x;
+  if (gate_flag && *gate_flag == 0) {
+    // every row of the batch equals row 0 (the drop-in's tiled-window case, inference.py:144): broadcast its latent
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < (long long)n_frames * kLatent; i += (long long)gridDim.x * blockDim.x)
+      latent[i] = lat0[i & (kLatent - 1)];
+    return;
+  }
+  for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+  __syncthreads();                 // the previous frame's shared-memory state is no longer read
   if (tid < 10) {
     float s = 0.f, c = 1.f;
     if (frame_idx) {
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
   }
   __syncthreads();
   }
-  if (!frame_bias) return;
+  if (!frame_bias) continue;
   {
     // bias0 = b_uv + (Wa a + b_a) + (Wt t + b_t)   (tf_nerf.py:252-258, same association order)
     const int n = tid;
@@ -131,6 +140,7 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     fb[512 + n] = (float)(a0 + (double)Fp[F_PTS_B + 0 * 256 + n]);
     fb[768 + n] = (float)(a5 + (double)Fp[F_PTS_B + 5 * 256 + n]);
   }
+  }   // frames
 }
 
 }  // namespace s2l
@@ -147,7 +157,7 @@ extern "C" int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, in
   if (n_frames == 0) return 0;
   audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed,
-      reinterpret_cast<const long long*>(frame_idx), latent, frame_bias, nullptr, 0);
+      reinterpret_cast<const long long*>(frame_idx), latent, frame_bias, nullptr, 0, n_frames, nullptr, nullptr);
   return check_launch("audio_encode_kernel") ? 0 : 5;
 }
 
@@ -158,7 +168,7 @@ extern "C" int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, in
   if (n_frames == 0) return 0;
   audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(blob), blob_layout(), nullptr, 0, reinterpret_cast<const long long*>(frame_idx), nullptr,
-      frame_bias, latent, (long long)latent_stride);
+      frame_bias, latent, (long long)latent_stride, n_frames, nullptr, nullptr);
   return check_launch("audio_encode_kernel(latent)") ? 0 : 5;
 }
 
@@ -188,4 +198,26 @@ extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_s
   const int grid = (int)((total + 256 * 8 - 1) / (256 * 8) < 148 * 8 ? (total + 256 * 8 - 1) / (256 * 8) : 148 * 8);
   rows_differ_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
   return check_launch("rows_differ_kernel") ? 0 : 5;
+}
+
+// Drop-in audio_merge_forward without host synchronisation: the unmodified inference loop hands AudioNet the SAME window
+// H*W times (inference.py:144).  A compare kernel sets a device flag; row 0 is encoded once; then ONE persistent launch
+// either broadcasts that latent to every row (flag 0) or encodes every row (flag 1) — decided on the device.
+extern "C" size_t s2l_audio_merge_auto_scratch_bytes(void) { return 64 * sizeof(float) + 256; }
+extern "C" int32_t s2l_audio_merge_auto(const void* blob, const float* audio, int32_t transposed, int64_t n_rows, float* latent,
+                                        void* scratch, void* stream) {
+  if (!blob || !scratch || (n_rows > 0 && (!audio || !latent))) { set_error("s2l_audio_merge_auto: null argument"); return 1; }
+  if (n_rows < 0 || n_rows > 0x7fffffff) { set_error("s2l_audio_merge_auto: bad n_rows"); return 2; }
+  if (n_rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* lat0 = reinterpret_cast<float*>(scratch);
+  int32_t* flag = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(scratch) + 64 * sizeof(float));
+  int rc = s2l_rows_differ(audio, n_rows, kAudioWin * kAudioFeat, 0, kAudioWin * kAudioFeat, flag, stream);
+  if (rc) return rc;
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(blob);
+  audio_encode_kernel<<<1, 256, 0, st>>>(b, blob_layout(), audio, transposed, nullptr, lat0, nullptr, nullptr, 0, 1, nullptr, nullptr);
+  if (!check_launch("audio_encode_kernel(row 0)")) return 5;
+  const int grid = (int)(n_rows < 148 * 8 ? n_rows : 148 * 8);
+  audio_encode_kernel<<<grid, 256, 0, st>>>(b, blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, (int)n_rows, flag, lat0);
+  return check_launch("audio_encode_kernel(auto)") ? 0 : 5;
 }

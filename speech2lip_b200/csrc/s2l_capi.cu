@@ -54,12 +54,13 @@ int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const f
 int launch_tile_scan(const int* count, int F, int Sc, int* ts128, int* ts64, cudaStream_t st);
 int launch_flag_last(const float* raw, int F, int R, int S, float thr, int* count, int* rays, cudaStream_t st);
 int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, long long time_idx, int has_time,
-                         float* out, float* save, int uv_dims, int out_ch, cudaStream_t st);
+                         float* out, float* save, int uv_dims, int out_ch, cudaStream_t st, const Gate* gate = nullptr,
+                         const long long* time_idx_dev = nullptr);
 int launch_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts, long long n_rows, float* dsave,
                         int out_ch, cudaStream_t st);
 int launch_embed(const float* x, long long n_rows, int row_stride, int uv_dims, float* pe, cudaStream_t st);
 int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
-                  int npass, cudaStream_t st, const TcEpi* epi = nullptr);
+                  int npass, cudaStream_t st, const TcEpi* epi = nullptr, const Gate* gate = nullptr);
 
 static long long points_per_frame(const S2LGeom& g) {
   switch (g.pts_mode) {
@@ -165,6 +166,39 @@ extern "C" int32_t s2l_rgb_forward_rows(const void* blob, const float* x, int64_
   if (n_rows < 0) { set_error("s2l_rgb_forward_rows: negative n_rows"); return 2; }
   if ((uv_dims != 2 && uv_dims != 3) || out_ch < 1 || out_ch > 4) { set_error("s2l_rgb_forward_rows: unsupported dims uv_dims=%d out_ch=%d", uv_dims, out_ch); return 2; }
   return launch_mlp_fp32_rows(blob, x, n_rows, time_idx, has_time, out, nullptr, uv_dims, out_ch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Drop-in rgb_forward without host synchronisation (include/speech2lip_b200.h): compare kernel -> device flag; the
+// constant-latent tensor-core path and the general per-row fp32 path are BOTH enqueued, each gated on the flag.
+extern "C" size_t s2l_rgb_forward_auto_scratch_bytes(void) { return 4 * 256 * sizeof(float) + 256; }
+extern "C" int32_t s2l_rgb_forward_auto(const void* blob, const float* x, int64_t n_rows, const int64_t* time_idx_dev, float* out,
+                                        int32_t uv_dims, int32_t out_ch, int32_t precision, void* scratch, void* stream) {
+  if (!blob || (n_rows > 0 && (!x || !out)) || !scratch) { set_error("s2l_rgb_forward_auto: null argument"); return 1; }
+  if (n_rows < 0) { set_error("s2l_rgb_forward_auto: negative n_rows"); return 2; }
+  if ((uv_dims != 2 && uv_dims != 3) || out_ch < 1 || out_ch > 4) { set_error("s2l_rgb_forward_auto: unsupported dims uv_dims=%d out_ch=%d", uv_dims, out_ch); return 2; }
+  const int np = precision == S2L_PREC_BF16X3 ? 3 : precision == S2L_PREC_FP16F8 ? 2 : precision == S2L_PREC_BF16X1 ? 1 : 0;
+  if (n_rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (np == 0)      // exact precision requested: the general kernel serves both cases
+    return launch_mlp_fp32_rows(blob, x, n_rows, 0, time_idx_dev ? 1 : 0, out, nullptr, uv_dims, out_ch, st, nullptr,
+                                reinterpret_cast<const long long*>(time_idx_dev));
+  float* bias = reinterpret_cast<float*>(scratch);
+  int32_t* flag = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(scratch) + 4 * 256 * sizeof(float));
+  const int stride = uv_dims + kLatent;
+  int rc = s2l_rows_differ(x, n_rows, stride, uv_dims, kLatent, flag, stream);
+  if (rc) return rc;
+  if ((rc = s2l_latent_bias_fwd(blob, x + uv_dims, stride, time_idx_dev, bias, 1, stream))) return rc;
+  PointSrc src{};
+  src.mode = S2L_PTS_EXPLICIT;
+  src.uv_dims = uv_dims;
+  src.S = src.Sc = 1;
+  src.P = n_rows;
+  src.pts = x;
+  src.pts_stride = stride;
+  const Gate g_const{flag, 0}, g_rows{flag, 1};
+  if ((rc = launch_mlp_tc(blob, src, 1, bias, out, out_ch, np, st, nullptr, &g_const))) return rc;
+  return launch_mlp_fp32_rows(blob, x, n_rows, 0, time_idx_dev ? 1 : 0, out, nullptr, uv_dims, out_ch, st, &g_rows,
+                              reinterpret_cast<const long long*>(time_idx_dev));
 }
 
 extern "C" int32_t s2l_rgb_forward_rows_train(const void* blob, const float* x, int64_t n_rows, int64_t time_idx,

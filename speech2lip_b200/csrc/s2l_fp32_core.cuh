@@ -37,6 +37,8 @@ struct Fp32Args {
   const float4* fix_carry;      // [F*R] (T_last, acc rgb) left by the fused compositing epilogue -> fix_rgb [F*R,3] is rewritten
   float* fix_rgb;
   float* patch_raw;             // unfused path instead: the exact outputs overwrite raw [F*R, S, 4] at sample S - 1
+  Gate gate;                    // optional device-side launch gate (s2l_points.cuh)
+  const long long* time_idx_dev;   // ROWLAT: time index read on the device (overrides time_idx when set)
 };
 
 struct Pipe {

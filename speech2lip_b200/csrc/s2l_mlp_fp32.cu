@@ -12,6 +12,7 @@ namespace s2l {
 
 template <bool ROWLAT>
 __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant__ Fp32Args a) {
+  if (a.gate.flag && *a.gate.flag != a.gate.value) return;      // gated launch: the other implementation serves this call
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* X = reinterpret_cast<float*>(smem_raw);
   float* Y = X + 256 * TMP;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(const __grid_constant_
     if (tid < 10) {
       float s = 0.f, c = 1.f;
       if (a.has_time) {
-        const float ang = __fmul_rn((float)a.time_idx, Cc[C_DIV + tid]);
+        const float ang = __fmul_rn((float)(a.time_idx_dev ? a.time_idx_dev[0] : a.time_idx), Cc[C_DIV + tid]);
         s = sinf(ang);
         c = cosf(ang);
       }
@@ -268,8 +269,11 @@ int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const f
 }
 
 int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, long long time_idx, int has_time,
-                         float* out, float* save, int uv_dims, int out_ch, cudaStream_t st) {
+                         float* out, float* save, int uv_dims, int out_ch, cudaStream_t st, const Gate* gate,
+                         const long long* time_idx_dev) {
   Fp32Args a{};
+  if (gate) a.gate = *gate;
+  a.time_idx_dev = time_idx_dev;
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
   a.src = PointSrc{};

@@ -62,6 +62,7 @@ static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
 // (s2l_train_dgrad.cu, s2l_train_wgrad.cu).
 template <int NPASS, int UVD, int CL, bool TRAIN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
+  if (a.gate.flag && *a.gate.flag != a.gate.value) return;      // gated launch: the other implementation serves this call
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T1_SM_BAR);
   uint64_t* b_full = bars;
@@ -552,8 +553,9 @@ static long long* g_timeline = nullptr;
 extern "C" void s2l_debug_set_timeline(long long* buf) { g_timeline = buf; }     // debug builds (tools/tc_timeline.py)
 
 int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* out, int out_ch,
-                  int npass, cudaStream_t st, const TcEpi* epi) {
+                  int npass, cudaStream_t st, const TcEpi* epi, const Gate* gate) {
   TcArgs a{};
+  if (gate) a.gate = *gate;
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
   a.src = src;

@@ -102,6 +102,7 @@ __host__ __device__ constexpr uint32_t idesc2(uint32_t a_fmt, uint32_t b_fmt, in
 template <int NPASS, int UVD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tm8,
                                                                                             const __grid_constant__ CUtensorMap tm4) {
+  if (a.gate.flag && *a.gate.flag != a.gate.value) return;      // gated launch: the other implementation serves this call
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_SM_BAR);
   uint64_t* b_empty = bars + T2_BEMPTY;

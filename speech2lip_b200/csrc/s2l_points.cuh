@@ -14,7 +14,8 @@ struct PointSrc {
   float eps;            // GRID_ENS4 eps_shift
   const float* eps_pf;  // optional per-frame eps_shift [F]
   long long P;          // point evaluations per frame (RAYS: R * Sc)
-  const float* pts;     // EXPLICIT: [F*P, uv_dims]
+  const float* pts;     // EXPLICIT: [F*P, uv_dims] (row stride pts_stride floats; 0 = uv_dims)
+  int pts_stride;
   const float* rays_o;  // RAYS
   const float* rays_d;
   const float* z;
@@ -30,6 +31,13 @@ struct PointSrc {
 
 // Per-pixel reduction fused into the tensor-core kernels' output-layer epilogue (reduce_tile, s2l_tc_common.cuh)
 enum { EPI_RAW = 0, EPI_ENS4 = 1, EPI_COMPOSITE = 2 };
+// Device-side launch gate: a kernel whose gate pointer is set does its work only when *gate == gate_value and exits at
+// once otherwise.  Lets a host call enqueue BOTH implementations of a data-dependent choice (constant-latent tensor-core
+// path / general per-row path of the drop-in rgb_forward) without reading the deciding flag back.
+struct Gate {
+  const int* flag;
+  int value;
+};
 struct TcEpi {
   int mode;                  // EPI_*
   float* rgb;                // [F, H*W, 3]
@@ -80,7 +88,7 @@ __device__ __forceinline__ void gen_point(const PointSrc& s, int f, long long p,
     for (int d = 0; d < 3; ++d)
       x[d] = __fadd_rn(s.rays_o[rrow * 3 + d], __fmul_rn(s.rays_d[rrow * 3 + d], zz));
   } else {
-    const float* q = s.pts + ((long long)f * s.P + p) * s.uv_dims;
+    const float* q = s.pts + ((long long)f * s.P + p) * (s.pts_stride ? s.pts_stride : s.uv_dims);
     for (int d = 0; d < s.uv_dims; ++d) x[d] = q[d];
   }
 }

@@ -50,6 +50,7 @@ struct TcArgs {
   __nv_bfloat16* save_h;     // [8][rows_total][256] post-ReLU activations h0..h7 exactly as the next layer's MMA consumed them
   __nv_bfloat16* save_pe;    // [rows_total][64] positional encodings (bf16), the B operand of the fold weight gradients
   long long rows_total;      // n_tiles * 128
+  Gate gate;                 // optional device-side launch gate (s2l_points.cuh)
 };
 
 

@@ -129,6 +129,36 @@ def rows_constant(x, col0, ncols):
     return int(flag.item()) == 0
 
 
+def audio_merge_auto(w, audio, scratch):
+    """TalkingFace.audio_merge_forward for a possibly tiled batch (inference.py:144), decided on the device: no host sync."""
+    lib = _cabi.lib()
+    audio = _f32c(audio, "audio")
+    if audio.dim() != 3 or audio.shape[1] * audio.shape[2] != 16 * 29:
+        raise ValueError("audio must be [B,16,29] or [B,29,16], got %s" % (tuple(audio.shape),))
+    B = audio.shape[0]
+    latent = torch.empty(B, 64, device=audio.device)
+    with torch.cuda.device(audio.device):
+        _cabi.check(lib.s2l_audio_merge_auto(_ptr(w.blob), _ptr(audio), 1 if audio.shape[2] == 16 else 0, B, _ptr(latent),
+                                             _ptr(scratch), _stream()), "s2l_audio_merge_auto")
+    return latent
+
+
+def rgb_forward_auto(w, x, time_pts, precision, scratch):
+    """TalkingFace.rgb_forward without a host sync: constant-latent rows -> fused tensor-core MLP in `precision`, arbitrary
+    latents -> general fp32 kernel; the choice is made on the device.  time_pts: tensor / int / None (only element 0 is used,
+    tf_nerf.py:439)."""
+    lib = _cabi.lib()
+    x = _f32c(x, "uv_audio_pts")
+    out = torch.empty(x.shape[0], w.out_ch, device=x.device)
+    tdev = None
+    if time_pts is not None:
+        tdev = torch.as_tensor(time_pts).reshape(-1)[:1].to(device=x.device, dtype=torch.int64, non_blocking=True)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_rgb_forward_auto(_ptr(w.blob), _ptr(x), x.shape[0], _ptr(tdev), _ptr(out), w.uv_dims, w.out_ch,
+                                             _cabi.PRECISIONS[precision], _ptr(scratch), _stream()), "s2l_rgb_forward_auto")
+    return out
+
+
 def rgb_forward_const_latent(w, x, time_idx=None, precision="bf16x3"):
     """TalkingFace.rgb_forward for the caller pattern of inference.py:144-158 — every row of x [N, uv_dims+64] carries
     the SAME latent (checked by the caller): per-frame constants from row 0's latent, then the fused tensor-core MLP

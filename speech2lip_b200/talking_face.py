@@ -175,6 +175,8 @@ class TalkingFace(nn.Module):
         # the exact CUDA-core kernel; set `dropin_fast_path = False` to always take the general per-row path.
         self.dropin_fast_path = os.environ.get("S2L_DROPIN_FAST", "1") != "0"
         self.dropin_precision = os.environ.get("S2L_DROPIN_PRECISION", "bf16x3")
+        if self.dropin_precision not in ("bf16x3", "fp16f8", "fp32"):
+            raise ValueError("S2L_DROPIN_PRECISION must be bf16x3, fp16f8 (parity modes) or fp32, got %r" % self.dropin_precision)
         self.dropin_min_rows = 1024
 
     # ------------------------------------------------------------------ packed weights (kernel layout)
@@ -218,30 +220,37 @@ class TalkingFace(nn.Module):
                 cols = cols.permute(0, 2, 1, 3).reshape(x.shape[0], cols.shape[2], -1)   # [B,T/2,C*3]
                 x = F.leaky_relu(cols @ conv.weight.reshape(conv.weight.shape[0], -1).t() + conv.bias, 0.02).permute(0, 2, 1)
             return self.encoder_fc1(x.squeeze(-1))
-        if (self.dropin_fast_path and audio.is_cuda and audio.dim() == 3 and audio.shape[0] >= self.dropin_min_rows
-                and R.rows_constant(audio, 0, audio.shape[1] * audio.shape[2])):
-            # inference.py:144 tiles ONE window H*W times: encode it once (AudioNet is bit-invariant to batch tiling)
-            latent, _ = R.audio_encode(self.packed_weights(), audio[:1], None, want_latent=True, want_bias=False)
-            return latent.expand(audio.shape[0], -1).contiguous()      # a fresh, ordinarily-strided [B,64] like the reference's
+        if self.dropin_fast_path and audio.is_cuda and audio.dim() == 3 and audio.shape[0] >= self.dropin_min_rows:
+            # inference.py:144 tiles ONE window H*W times: a compare kernel decides ON THE DEVICE whether row 0's latent is
+            # broadcast or every row is encoded (AudioNet is bit-invariant to batch tiling) — no host synchronisation
+            return R.audio_merge_auto(self.packed_weights(), audio, self._dropin_scratch(audio.device))
         latent, _ = R.audio_encode(self.packed_weights(), audio, None, want_latent=True, want_bias=False)
         return latent
 
     def rgb_forward(self, uv_audio_pts, time_pts=None, head_pose_pts=None, rgb_pts=None, lms_pts=None, text_pts=None):
         """tf_nerf.py:225-285.  uv_audio_pts [N, uv_dims+64]; time_pts: only element 0 is used (tf_nerf.py:439)."""
-        t = None
-        if time_pts is not None:
-            t = int(torch.as_tensor(time_pts).reshape(-1)[0].item())
         if self._needs_grad(uv_audio_pts):
+            t = None if time_pts is None else int(torch.as_tensor(time_pts).reshape(-1)[0].item())
             from .autograd import rgb_forward_train      # fused fp32 forward (saves activations) + fused dgrad kernel
             return rgb_forward_train(self, uv_audio_pts, t)
         x = uv_audio_pts
-        if (self.dropin_fast_path and isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2
-                and x.shape[0] >= self.dropin_min_rows and x.shape[1] == self.uv_dims + 64
-                and R.rows_constant(x, self.uv_dims, 64)):
-            # inference.py:150-158: the same latent in every row -> hoist the audio/time terms and run the fused
-            # tensor-core MLP (parity mode `dropin_precision`) instead of the general per-row-latent fp32 path
-            return R.rgb_forward_const_latent(self.packed_weights(), x, t, self.dropin_precision)
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.shape[1] == self.uv_dims + 64:
+            # No host synchronisation: the time index stays on the device and a compare kernel decides there whether the rows
+            # share one latent (inference.py:150-158: hoist the audio/time terms, fused tensor-core MLP in the parity mode
+            # `dropin_precision`, ~1e-4 from the exact result) or carry arbitrary latents (general exact fp32 kernel).
+            # Fewer than dropin_min_rows rows, or dropin_fast_path = False, always take the exact kernel.
+            fast = self.dropin_fast_path and x.shape[0] >= self.dropin_min_rows
+            return R.rgb_forward_auto(self.packed_weights(), x, time_pts, self.dropin_precision if fast else "fp32",
+                                      self._dropin_scratch(x.device))
+        t = None if time_pts is None else int(torch.as_tensor(time_pts).reshape(-1)[0].item())
         return R.rgb_forward_rows(self.packed_weights(), uv_audio_pts, t)
+
+    def _dropin_scratch(self, device):
+        sc = self.__dict__.get("_dropin_sc")
+        if sc is None or sc.device != device:
+            sc = torch.empty(8192, dtype=torch.uint8, device=device)
+            self.__dict__["_dropin_sc"] = sc
+        return sc
 
     def render_lip_train(self, audio, index, H, W, eps_shift=None):
         """F lip frames through the 4-tap local ensemble in ONE differentiable launch sequence on tensor cores (bf16):
@@ -250,6 +259,15 @@ class TalkingFace(nn.Module):
         audio [F,16,29], index [F] (time_pts of each frame) -> rgb [F,H,W,3]."""
         from .autograd import render_lip_train
         return render_lip_train(self, audio, index, H, W, eps_shift)
+
+    def render_sync_window_train(self, audio_window, index, total_frame, H, W, eps_shift=None):
+        """The sync-expert loss window WITH gradients (training.py:500-525): T consecutive lip frames, frame t rendered with
+        audio_window[t], time index min(index + t, total_frame - 1) and its own eps_shift draw (drawn in frame order from the
+        device RNG exactly as T predict_lip_image calls would) — one differentiable launch sequence instead of T x 4
+        rgb_forward calls.  audio_window [T,16,29] -> [T,H,W,3]."""
+        T = audio_window.shape[0]
+        idx = torch.clamp(torch.arange(T) + int(index), max=int(total_frame) - 1)
+        return self.render_lip_train(audio_window, idx, H, W, eps_shift)
 
     def renderer(self, precision="bf16x3"):
         """Batched frame renderer (not expressible through the reference's per-call contract)."""

@@ -288,3 +288,30 @@ def test_train_render_batch_equals_single_frames_and_is_deterministic(S):
         assert rel(d1[0], dl[f]) < 1e-5
         acc = G1 if acc is None else {k: acc[k] + G1[k] for k in acc}
     assert max(rel(acc[k], G[k]) for k in G) < 1e-4
+
+
+def test_sync_window_render_with_gradients(S):
+    """training.py:500-548 needs gradients through the five window renders: render_sync_window_train == the forward-only
+    one-launch window render (same indices clamped at total_frame - 1, same per-frame eps) up to bf16, carries a grad_fn, and
+    its eps_shift draws consume the device RNG exactly like five predict_lip_image calls."""
+    import json
+    cfg = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg).to(dev()).train()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming", 2, 3).items()}, strict=False)
+    H, W, T = 16, 24, 5
+    win = torch.from_numpy(synth.make_audio(T, seed=71)).to(dev())
+    torch.manual_seed(5)
+    eps_expected = torch.cat([(0.5 / H) * torch.rand(1, device=dev()) / 2.0 for _ in range(T)])       # training.py:198-200, five calls
+    torch.manual_seed(5)
+    got = m.render_sync_window_train(win, index=97, total_frame=100, H=H, W=W)
+    assert got.requires_grad and got.shape == (T, H, W, 3)
+    with torch.no_grad():
+        want = m.renderer("bf16x3").render_sync_window(win, 97, 100, H, W, eps_expected)
+    scale = want.abs().max().item()
+    e = (got.detach() - want).abs().max().item()
+    print("sync window with gradients vs forward-only window render: %.2e (scale %.2f)" % (e, scale))
+    assert e < 1.5e-2 * scale
+    got.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0 for p in m._hot_params().values())
+    # frames 3 and 4 share the clamped time index 99 but not their audio windows
+    assert not torch.equal(got[3], got[4])
