@@ -173,15 +173,27 @@ extern "C" int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, in
 }
 
 namespace s2l {
-// flag[0] = 1 when any row differs (bitwise) from row 0 in columns [col0, col0 + ncols); the caller zeroes flag first
+// flag[0] = 1 when any row differs (bitwise) from row 0 in columns [col0, col0 + ncols); the caller zeroes flag first.
+// One warp per row (grid-stride over rows), lanes stride over the row in 8-byte words when the geometry allows it
+// (row stride, col0 and ncols even, base 8-byte aligned: the drop-in's [N,66] rows and [B,464] windows both qualify).
+template <typename V>
 __global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __restrict__ x, long long n_rows, long long row_stride,
                                                           int col0, int ncols, int* __restrict__ flag) {
-  const long long total = n_rows * ncols;
+  constexpr int VW = sizeof(V) / 4;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nv = ncols / VW;
+  const V* r0 = reinterpret_cast<const V*>(x + col0);
   bool diff = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / ncols;
-    const int c = (int)(i - r * ncols);
-    diff |= x[r * row_stride + col0 + c] != x[col0 + c];
+  for (long long r = warp + 1; r < n_rows; r += n_warps) {
+    const V* rr = reinterpret_cast<const V*>(x + r * row_stride + col0);
+    for (int j = lane; j < nv; j += 32) {
+      const V a = rr[j], b = __ldg(r0 + j);
+      if (VW == 2) diff |= (reinterpret_cast<const uint2&>(a).x != reinterpret_cast<const uint2&>(b).x) |
+                           (reinterpret_cast<const uint2&>(a).y != reinterpret_cast<const uint2&>(b).y);
+      else diff |= reinterpret_cast<const uint32_t&>(a) != reinterpret_cast<const uint32_t&>(b);
+    }
   }
   if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flag, 1);
 }
@@ -194,9 +206,11 @@ extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_s
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
   if (n_rows <= 1 || ncols == 0) return 0;
-  const long long total = n_rows * ncols;
-  const int grid = (int)((total + 256 * 8 - 1) / (256 * 8) < 148 * 8 ? (total + 256 * 8 - 1) / (256 * 8) : 148 * 8);
-  rows_differ_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
+  const long long want = (n_rows + 7) / 8;                                   // 8 warps per block, one row per warp per pass
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  const bool wide = (row_stride % 2 == 0) && (col0 % 2 == 0) && (ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+  if (wide) rows_differ_kernel<uint2><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
+  else rows_differ_kernel<uint32_t><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
   return check_launch("rows_differ_kernel") ? 0 : 5;
 }
 

@@ -193,7 +193,14 @@ class TalkingFace(nn.Module):
         """PackedWeights for the current parameter values; re-packed when any hot-path tensor changed
         (in-place optimizer steps and load_state_dict bump tensor._version)."""
         hp = self._hot_params()
-        key = tuple((v.data_ptr(), v._version) for v in hp.values())
+        # in-place updates (optimizer steps, load_state_dict, p.add_()) bump tensor._version; a replaced storage (module.to())
+        # changes data_ptr.  `.data` edits bypass the version counter: call invalidate_packed() after those.
+        vals = self.__dict__.get("_hot_vals")
+        if vals is None or vals[0] is not hp["encoder_conv.0.weight"]:
+            vals = self.__dict__["_hot_vals"] = list(hp.values())
+        key = [v._version for v in vals]
+        key.append(vals[0].data_ptr())
+        key.append(vals[-1].data_ptr())
         if self._packed is None or key != self._packed_key:
             if self._packed is None:
                 self._packed = R.PackedWeights(hp, self.uv_dims, self.output_ch)
@@ -201,6 +208,11 @@ class TalkingFace(nn.Module):
                 self._packed.repack(hp)
             self._packed_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        """Forces the next call to re-pack the kernel-layout weights (needed only after edits through `param.data`, which do
+        not bump the version counter packed_weights() watches)."""
+        self._packed_key = None
 
     def _needs_grad(self, *tensors):
         return torch.is_grad_enabled() and (any(p.requires_grad for p in self._hot_params().values())

@@ -1,51 +1,40 @@
-"""Frames/s of the UNMODIFIED caller: the literal inference.py:144-159 call sequence (tile the audio window H*W times,
-audio_merge_forward, cat with the uv grid, rgb_forward) through the TalkingFace drop-in, one frame per iteration, next to
-the batched LipRenderer on the same frames.  usage: bench_dropin.py [size] [frames]"""
+"""The UNMODIFIED caller loop (inference.py:144-159 call sequence) through the TalkingFace drop-in: frames/s, and a check that
+no torch-level host synchronisation happens inside the loop body (torch.cuda.set_sync_debug_mode)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import speech2lip_b200 as s2l
-from oracle import synth, s2l_oracle as O
-
-size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+from speech2lip_b200 import synth
 dev = torch.device("cuda:0")
+H = W = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
-m = s2l.TalkingFace(device=dev, cfg=cfg, mode="eval").to(dev).eval()
-m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming").items()}, strict=False)
-H = W = size
-windows = torch.from_numpy(synth.make_audio(n_frames, seed=3)).to(dev)
-coords = torch.from_numpy(O.get_coords(W, H).numpy()).to(dev)
-
+tf = s2l.TalkingFace(device=dev, cfg=cfg, mode="eval").to(dev).eval()
+tf.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming", 2, 3).items()}, strict=False)
+wins = torch.from_numpy(synth.make_audio(64, seed=9)).to(dev)
+vv, uu = torch.meshgrid(torch.linspace(0.0, 1.0, H, device=dev), torch.linspace(0.0, 1.0, W, device=dev), indexing="ij")
+coords = torch.stack([uu, vv], -1).view(-1, 2)
+idx = [torch.tensor([i], device=dev) for i in range(64)]
 
 def frame(i):
-    audio = windows[i:i + 1].tile(H * W, 1, 1)                                    # inference.py:144
     with torch.no_grad():
-        ab = m.audio_merge_forward(audio)                                         # :150
-        x = torch.cat([coords[:, None, :], ab[:, None, :]], -1)                   # :151
-        out = m.rgb_forward(x.view(-1, m.audio_dims + 2), time_pts=torch.tensor([i], device=dev), rgb_pts=None)   # :158
-    return out[:, :3]
-
-
-for i in range(3):
+        au = wins[i:i + 1].tile(H * W, 1, 1)
+        ab = tf.audio_merge_forward(au)
+        xx = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, tf.audio_dims + 2)
+        return tf.rgb_forward(xx, time_pts=idx[i], rgb_pts=None)[:, :3]
+for i in range(4):
     frame(i)
 torch.cuda.synchronize()
-t0 = time.perf_counter()
-for i in range(n_frames):
-    out = frame(i)
+torch.cuda.set_sync_debug_mode("error")
+for i in range(4):
+    frame(i)                      # raises if any torch op in the body synchronises with the host
+torch.cuda.set_sync_debug_mode("default")
 torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-print("drop-in TalkingFace loop (inference.py:144-159), %dx%d: %.1f frames/s (%.3f ms/frame)" % (H, W, n_frames / dt, dt / n_frames * 1e3))
-
-r = m.renderer("bf16x3")
-idx = torch.arange(n_frames)
-ref = r.render_frames(windows, idx, H, W)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-ref = r.render_frames(windows, idx, H, W)
-torch.cuda.synchronize()
-dt2 = time.perf_counter() - t0
-print("batched LipRenderer (bf16x3), same frames: %.1f frames/s" % (n_frames / dt2))
-last = frame(n_frames - 1).reshape(H, W, 3)
-print("max-abs drop-in vs batched renderer on the last frame: %.2e" % (last - ref[-1]).abs().max().item())
+for prec in ("bf16x3", "fp16f8"):
+    tf.dropin_precision = prec
+    t0 = time.perf_counter()
+    for i in range(64):
+        frame(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("drop-in loop %dx%d %s: %.0f frames/s (%.3f ms/frame), no host sync in the body" % (H, W, prec, 64 / dt, dt / 64 * 1e3))
