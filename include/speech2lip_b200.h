@@ -57,7 +57,13 @@ enum {
   S2L_PREC_BF16X3 = 1,  /* tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (parity)   */
   S2L_PREC_BF16X1 = 2,  /* tcgen05 single bf16 pass (fast, NOT within the 1e-3 parity bar)          */
   S2L_PREC_FP16F8 = 3   /* tcgen05 fp16 main product + two fp8 (e4m3/e5m2) correction products, fp32 accumulate:
-                           2 bf16-MMA equivalents per product, ~3e-4 max-abs on O(8) outputs (parity)  */
+                           2 bf16-MMA equivalents per product, ~3e-4 max-abs on O(8) outputs (parity).
+                           VALIDATED DOMAIN: every tensor-core weight |w| < 1024 and every hidden activation |a| < 4096 (beyond
+                           that the scaled fp8 residuals saturate and the correction terms are silently lost; fp16 itself
+                           overflows at 65504).  s2l_pack_weights records the weight side (s2l_blob_meta); the host layer
+                           refuses fp16f8 outside it and falls back to S2L_PREC_BF16X3 with a logged warning
+                           (speech2lip_b200.LipRenderer); activations can be probed with the exact path
+                           (LipRenderer.probe_fp16f8_domain) or counted in a -DS2L_DBG_SATCOUNT build.             */
 };
 
 /* How the kernel obtains the coordinates of point-evaluation p of frame f. */
@@ -91,8 +97,10 @@ typedef struct S2LGeom {
   float   term_thr;        /* early-ray-termination threshold on the transmittance (e.g. 1e-4); <= 0 with C > 1: chunked, never terminates */
   float   fix_thr;         /* tensor-core precisions: rays whose LAST sample's density is within fix_thr of zero are re-evaluated
                               in exact fp32 (density2outputs gives the last sample delta = 1e10, rendering.py:44, so alpha_last is a
-                              step function of sign(sigma_last) and a rounding error there flips the pixel).  0 -> default 2e-3
-                              (3x the worst tensor-core density error measured), < 0 -> off                                    */
+                              step function of sign(sigma_last) and a rounding error there flips the pixel).  0 -> automatic:
+                              2e-3 * max(1, |output_linear.weight[3]|_2 / sqrt(2)) computed at pack time (2e-3 = 3x the worst
+                              tensor-core density error measured on kaiming-scale weights; the error scales with the density
+                              row), < 0 -> off                                                                               */
 } S2LGeom;
 
 /* Thread-local description of the last error (never NULL). */
@@ -101,6 +109,12 @@ int32_t     s2l_abi_version(void);
 
 /* PositionalEncodingTime.div_term (tf_nerf.py:431-432), 10 fp32 values, host-side helper. */
 void s2l_time_div_term(float* out10_host);
+
+/* What s2l_pack_weights recorded about the packed model (synchronises `stream`; call once per pack, not per frame):
+ * max |w| over the tensor-core weights incl. the folded input layers, how many of them leave the fp16f8 domain
+ * (|w| >= 1024), the L2 norm of output_linear's density row and the automatic fix_thr derived from it.  Any out pointer may be NULL. */
+int32_t s2l_blob_meta(const void* blob, float* max_abs_weight, int32_t* n_saturating_weights, float* density_row_norm,
+                      float* auto_fix_thr, void* stream);
 
 /* Size in bytes of the packed weight blob for a model with the given dims. */
 size_t s2l_blob_bytes(int32_t uv_dims, int32_t out_ch);

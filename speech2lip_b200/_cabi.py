@@ -41,6 +41,7 @@ SYMBOLS = {
     "s2l_abi_version": (C.c_int32, []),
     "s2l_time_div_term": (None, [C.POINTER(C.c_float)]),
     "s2l_blob_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "s2l_blob_meta": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
     "s2l_pack_weights": (C.c_int32, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "s2l_audio_encode_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

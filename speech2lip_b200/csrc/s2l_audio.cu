@@ -46,13 +46,9 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
   __shared__ float pe[kTimePE];
   __shared__ float b0s[256], bss[256];
   const int tid = threadIdx.x;
-  if (gate_flag && *gate_flag == 0) {
-    // every row of the batch equals row 0 (the drop-in's tiled-window case, inference.py:144): broadcast its latent
-    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < (long long)n_frames * kLatent; i += (long long)gridDim.x * blockDim.x)
-      latent[i] = lat0[i & (kLatent - 1)];
-    return;
-  }
-  for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+  const bool bcast = gate_flag && *gate_flag == 0;      // every row equals row 0 (the drop-in's tiled window, inference.py:144)
+  (void)lat0;
+  for (int f = bcast ? 0 : blockIdx.x; f < (bcast ? 1 : n_frames); f += gridDim.x) {
   __syncthreads();                 // the previous frame's shared-memory state is no longer read
   if (tid < 10) {
     float s = 0.f, c = 1.f;
@@ -96,18 +92,33 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     for (int k = 0; k < 64; ++k) acc = fmaf(A[A_FC2_W + tid * 64 + k], x5[k], acc);
     const float v = acc + A[A_FC2_B + tid];
     lat[tid] = v;
-    if (latent) latent[(size_t)f * kLatent + tid] = v;
+    if (latent && !bcast) latent[(size_t)f * kLatent + tid] = v;
   }
   __syncthreads();
+  if (bcast) {
+    // every CTA has just encoded row 0 itself (67 k MAC, cheaper than a second launch): broadcast it over its share of rows
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < (long long)n_frames * kLatent; i += (long long)gridDim.x * blockDim.x)
+      latent[i] = lat[i & (kLatent - 1)];
+    return;
+  }
   }
   if (!frame_bias) continue;
   {
     // bias0 = b_uv + (Wa a + b_a) + (Wt t + b_t)   (tf_nerf.py:252-258, same association order)
     const int n = tid;
     float ta = 0.f, tas = 0.f, tt = 0.f, tts = 0.f;
-    for (int k = 0; k < 64; ++k) {
-      ta = fmaf(C[C_FCA_WT + k * 256 + n], lat[k], ta);
-      tas = fmaf(C[C_FCAS_WT + k * 256 + n], lat[k], tas);
+    for (int k0 = 0; k0 < 64; k0 += 16) {
+      float wa[16], ws[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        wa[u] = __ldg(C + C_FCA_WT + (k0 + u) * 256 + n);
+        ws[u] = __ldg(C + C_FCAS_WT + (k0 + u) * 256 + n);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        ta = fmaf(wa[u], lat[k0 + u], ta);
+        tas = fmaf(ws[u], lat[k0 + u], tas);
+      }
     }
     float b0 = C[C_BIAS6 + 0 * 256 + n] + (ta + C[C_BIAS6 + 1 * 256 + n]);
     float bs = C[C_BIAS6 + 3 * 256 + n] + (tas + C[C_BIAS6 + 4 * 256 + n]);
@@ -131,10 +142,21 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     const int n = tid;
     const float* W0T = Fp + f_pts_off(0);
     const float* W5T = Fp + f_pts_off(5);
+    // (the blob is often cold here — a drop-in caller's 121 MB tiled window evicts it from L2 between frames — so the 2 x 256
+    //  loads are issued 16 deep per matrix instead of one dependent pair per iteration; the summation order is unchanged)
     double a0 = 0.0, a5 = 0.0;
-    for (int k = 0; k < 256; ++k) {
-      a0 += (double)W0T[k * 256 + n] * (double)b0s[k];
-      a5 += (double)W5T[k * 256 + n] * (double)bss[k];
+    for (int k0 = 0; k0 < 256; k0 += 16) {
+      float w0[16], w5[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        w0[u] = __ldg(W0T + (k0 + u) * 256 + n);
+        w5[u] = __ldg(W5T + (k0 + u) * 256 + n);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        a0 += (double)w0[u] * (double)b0s[k0 + u];
+        a5 += (double)w5[u] * (double)bss[k0 + u];
+      }
     }
     float* fb = frame_bias + (size_t)f * 4 * 256;
     fb[512 + n] = (float)(a0 + (double)Fp[F_PTS_B + 0 * 256 + n]);
@@ -190,9 +212,10 @@ __global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __rest
     const V* rr = reinterpret_cast<const V*>(x + r * row_stride + col0);
     for (int j = lane; j < nv; j += 32) {
       const V a = rr[j], b = __ldg(r0 + j);
-      if (VW == 2) diff |= (reinterpret_cast<const uint2&>(a).x != reinterpret_cast<const uint2&>(b).x) |
-                           (reinterpret_cast<const uint2&>(a).y != reinterpret_cast<const uint2&>(b).y);
-      else diff |= reinterpret_cast<const uint32_t&>(a) != reinterpret_cast<const uint32_t&>(b);
+      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+      for (int t = 0; t < VW; ++t) diff |= pa[t] != pb[t];
     }
   }
   if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flag, 1);
@@ -209,7 +232,9 @@ extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_s
   const long long want = (n_rows + 7) / 8;                                   // 8 warps per block, one row per warp per pass
   const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
   const bool wide = (row_stride % 2 == 0) && (col0 % 2 == 0) && (ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
-  if (wide) rows_differ_kernel<uint2><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
+  const bool wide4 = (row_stride % 4 == 0) && (col0 % 4 == 0) && (ncols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (wide4) rows_differ_kernel<uint4><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
+  else if (wide) rows_differ_kernel<uint2><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
   else rows_differ_kernel<uint32_t><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
   return check_launch("rows_differ_kernel") ? 0 : 5;
 }
@@ -229,9 +254,7 @@ extern "C" int32_t s2l_audio_merge_auto(const void* blob, const float* audio, in
   int rc = s2l_rows_differ(audio, n_rows, kAudioWin * kAudioFeat, 0, kAudioWin * kAudioFeat, flag, stream);
   if (rc) return rc;
   const uint8_t* b = reinterpret_cast<const uint8_t*>(blob);
-  audio_encode_kernel<<<1, 256, 0, st>>>(b, blob_layout(), audio, transposed, nullptr, lat0, nullptr, nullptr, 0, 1, nullptr, nullptr);
-  if (!check_launch("audio_encode_kernel(row 0)")) return 5;
-  const int grid = (int)(n_rows < 148 * 8 ? n_rows : 148 * 8);
+  const int grid = (int)(n_rows < 148 * 4 ? n_rows : 148 * 4);
   audio_encode_kernel<<<grid, 256, 0, st>>>(b, blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, (int)n_rows, flag, lat0);
   return check_launch("audio_encode_kernel(auto)") ? 0 : 5;
 }

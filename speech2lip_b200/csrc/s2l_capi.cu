@@ -52,7 +52,7 @@ int launch_mlp_fp32(const void* blob, const PointSrc& src, int n_frames, const f
                     int out_ch, cudaStream_t st, const float4* fix_carry = nullptr, float* fix_rgb = nullptr,
                     float* patch_raw = nullptr);
 int launch_tile_scan(const int* count, int F, int Sc, int* ts128, int* ts64, cudaStream_t st);
-int launch_flag_last(const float* raw, int F, int R, int S, float thr, int* count, int* rays, cudaStream_t st);
+int launch_flag_last(const float* raw, int F, int R, int S, float thr, const float* auto_thr, int* count, int* rays, cudaStream_t st);
 int launch_mlp_fp32_rows(const void* blob, const float* x, long long n_rows, long long time_idx, int has_time,
                          float* out, float* save, int uv_dims, int out_ch, cudaStream_t st, const Gate* gate = nullptr,
                          const long long* time_idx_dev = nullptr);
@@ -250,8 +250,8 @@ static RenderPlan make_plan(const S2LGeom& g, int precision, bool want_aux) {
     p.Sc = g.n_samples / g.sample_chunks;
   }
   p.fused = p.tc && ((rays && !want_aux && g.out_ch == 4 && chunk_ok(p.Sc)) || (g.pts_mode == S2L_PTS_GRID_ENS4 && g.out_ch == 3));
-  p.fix_thr = g.fix_thr == 0.f ? 2e-3f : g.fix_thr;
-  p.fix = rays && p.tc && precision != S2L_PREC_BF16X1 && p.fix_thr > 0.f;      // bf16x1 is a preview mode: no parity claim to protect
+  p.fix_thr = g.fix_thr == 0.f ? -1.f : g.fix_thr;      // -1 = the automatic threshold in the blob (META[3]); geom.fix_thr < 0 = off
+  p.fix = rays && p.tc && precision != S2L_PREC_BF16X1 && g.fix_thr >= 0.f;      // bf16x1 is a preview mode: no parity claim to protect
   p.term_thr = g.term_thr;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t o = 0;
@@ -347,7 +347,8 @@ extern "C" int32_t s2l_render_frames(const void* blob, const S2LGeom* geom, cons
     if (rc) return rc;
     if (pl.fix) {
       int* fcount = counts + (size_t)pl.chunks * F;
-      if ((rc = launch_flag_last(raw, F, R, geom->n_samples, pl.fix_thr, fcount, lists[0], st))) return rc;
+      const float* auto_thr = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(blob) + blob_layout().off_meta) + 3;
+      if ((rc = launch_flag_last(raw, F, R, geom->n_samples, pl.fix_thr, auto_thr, fcount, lists[0], st))) return rc;
       if ((rc = launch_tile_scan(fcount, F, 1, ts128, ts64, st))) return rc;
       fixsrc.list_rays = lists[0];
       if ((rc = launch_mlp_fp32(blob, fixsrc, F, bias, nullptr, 4, st, nullptr, nullptr, raw))) return rc;

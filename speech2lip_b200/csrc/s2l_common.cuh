@@ -103,8 +103,18 @@ constexpr int kTcwtBytes = (2 + kTLayers * 8) * kTGran;   // 950 272 B
 __host__ __device__ constexpr int t_layer_src(int i) { return 7 - i; }            // i-th dgrad layer reads pts_linears[7 - i]
 __host__ __device__ constexpr int t_layer_off(int i) { return (2 + i * 8) * kTGran; }
 
+// ---- META section (16 x 4 bytes, written by the pack kernels): the validated domain of the fp16f8 arithmetic and the
+//      model-dependent threshold of the last-sample re-evaluation
+//   [0] float  max |w| over every tensor-core weight (folded input layers included)
+//   [1] int    number of tensor-core weights with |w| >= kF8MaxWeight (their e4m3 residual saturates: correction lost)
+//   [2] float  L2 norm of output_linear's density row (0 when out_ch < 4)
+//   [3] float  automatic fix_thr = 2e-3 * max(1, [2] / sqrt(2)): the tensor-core density error scales with that row
+constexpr int kMetaWords = 16;
+constexpr float kF8MaxWeight = 1024.f;       // (w - fp16 w) * 2^kScaleW must stay below e4m3's 448: half an fp16 ulp at 1024 is 0.5
+constexpr float kF8MaxAct = 4096.f;          // (a - fp16 a) * 2^kScaleA below 448: half an fp16 ulp at 4096 is 2 (> 1.75)
+
 struct Layout {
-  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, off_tcw8, off_tcwt, total;
+  size_t off_audio, off_const, off_fp32, off_tcbias, off_tcw, off_dgrad, off_tcw8, off_tcwt, off_meta, total;
 };
 __host__ __device__ inline Layout blob_layout() {
   Layout L;
@@ -118,6 +128,7 @@ __host__ __device__ inline Layout blob_layout() {
   L.off_dgrad = o;  o = al(o + sizeof(float) * D_TOTAL);
   L.off_tcw8 = o;   o = al(o + kTcwBytes);
   L.off_tcwt = o;   o = al(o + kTcwtBytes);
+  L.off_meta = o;   o = al(o + kMetaWords * 4);
   L.total = o;
   return L;
 }

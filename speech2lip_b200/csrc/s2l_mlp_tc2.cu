@@ -537,3 +537,13 @@ int launch_mlp_tc2(const TcArgs& a, long long n_tiles, int npass, cudaStream_t s
 }
 
 }  // namespace s2l
+
+#ifdef S2L_DBG_SATCOUNT
+extern "C" unsigned long long s2l_debug_sat_count_tc2(void) {
+  unsigned long long v = 0, z = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&v, s2l::g_sat_count, sizeof(v));
+  cudaMemcpyToSymbol(s2l::g_sat_count, &z, sizeof(z));
+  return v;
+}
+#endif

@@ -1,6 +1,7 @@
 // s2l_pack_weights: PyTorch-layout fp32 parameters -> kernel-layout blob (see s2l_common.cuh).
 // Replaces the parameter inventory of TalkingFace.__init__ (tf_nerf.py:85-172) on the device side.
 #include <cmath>
+#include <cstring>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -55,6 +56,11 @@ __global__ void pack_relayout_kernel(ParamPtrs P, uint8_t* blob, Layout L, int E
     C[C_BIAS6 + 5 * 256 + i] = P.p[S2L_P_FC_TIME_SKIP_B][i];
   }
   for (int i = tid; i < 16; i += nth) C[C_DIV + i] = (i < 10) ? div_term.v[i] : 0.f;
+  // META: cleared here (this kernel runs first), filled by pack_tcw_kernel's atomics; the density-row norm by block 0
+  {
+    float* M = reinterpret_cast<float*>(blob + L.off_meta);
+    for (int i = tid; i < kMetaWords; i += nth) M[i] = 0.f;
+  }
 
   // FP32: W^T [K][256]
   for (int i = tid; i < 64 * 256; i += nth) {
@@ -151,6 +157,18 @@ __global__ void pack_tcw_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch
   } else {
     v = pts_w(P, g)[ng * 256 + kc * 64 + k];
   }
+  {
+    // fp16f8 domain bookkeeping (non-negative floats order like their bit patterns)
+    unsigned int* M = reinterpret_cast<unsigned int*>(blob + L.off_meta);
+    const float av = fabsf(v);
+    const unsigned act = __activemask();
+    const unsigned wmax = __reduce_max_sync(act, __float_as_uint(av));
+    const unsigned nsat = __popc(__ballot_sync(act, !(av < kF8MaxWeight)));
+    if ((threadIdx.x & 31) == (__ffs(act) - 1)) {      // one pair of atomics per warp
+      if (wmax) atomicMax(M + 0, wmax);
+      if (nsat) atomicAdd(M + 1, nsat);
+    }
+  }
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
   const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
   const int plane = (g == 8) ? kOutPlane : kGranPlane;
@@ -191,6 +209,19 @@ __global__ void pack_tcwt_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_c
   *reinterpret_cast<__nv_bfloat16*>(base + sw128_off(n, k)) = __float2bfloat16_rn(v);
 }
 
+__global__ void pack_meta_kernel(ParamPtrs P, uint8_t* blob, Layout L, int out_ch) {
+  float* M = reinterpret_cast<float*>(blob + L.off_meta);
+  float s = 0.f;
+  if (out_ch >= 4)
+    for (int k = threadIdx.x; k < 256; k += 32) { const float w = P.p[S2L_P_OUT_W][3 * 256 + k]; s = fmaf(w, w, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) {
+    const float nrm = sqrtf(s);
+    M[2] = nrm;
+    M[3] = 2e-3f * fmaxf(1.f, nrm / 1.41421356f);
+  }
+}
+
 }  // namespace s2l
 
 using namespace s2l;
@@ -199,6 +230,23 @@ using namespace s2l;
 extern "C" void s2l_time_div_term(float* out10) {
   const float c = (float)(-(std::log(10000.0) / 20.0));
   for (int i = 0; i < 10; ++i) out10[i] = std::exp((float)(2 * i) * c);
+}
+
+extern "C" int32_t s2l_blob_meta(const void* blob, float* max_abs_weight, int32_t* n_saturating_weights, float* density_row_norm,
+                                 float* auto_fix_thr, void* stream) {
+  if (!blob) { set_error("s2l_blob_meta: null blob"); return 1; }
+  float m[4];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemcpyAsync(m, reinterpret_cast<const uint8_t*>(blob) + blob_layout().off_meta, sizeof(m), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("s2l_blob_meta: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 5;
+  }
+  if (max_abs_weight) *max_abs_weight = m[0];
+  if (n_saturating_weights) { int32_t n; memcpy(&n, &m[1], 4); *n_saturating_weights = n; }
+  if (density_row_norm) *density_row_norm = m[2];
+  if (auto_fix_thr) *auto_fix_thr = m[3];
+  return 0;
 }
 
 extern "C" size_t s2l_blob_bytes(int32_t uv_dims, int32_t out_ch) {
@@ -236,5 +284,7 @@ extern "C" int32_t s2l_pack_weights(const float* const* params_host, void* blob,
   const long long n_t = (long long)(2 + kTLayers * 8) * 128 * 64;
   pack_tcwt_kernel<<<(unsigned)((n_t + 255) / 256), 256, 0, st>>>(P, b, L, out_ch);
   if (!check_launch("pack_tcwt_kernel")) return 5;
+  pack_meta_kernel<<<1, 32, 0, st>>>(P, b, L, out_ch);
+  if (!check_launch("pack_meta_kernel")) return 5;
   return 0;
 }

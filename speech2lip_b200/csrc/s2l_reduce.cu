@@ -185,10 +185,11 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(const int* __restrict__ 
 }
 
 // Unfused volumetric path: list the rays whose last-sample density (raw[ray, S-1, 3]) is within thr of zero.
-__global__ void flag_last_kernel(const float* __restrict__ raw, int F, int R, int S, float thr, int* __restrict__ count,
-                                 int* __restrict__ rays) {
+__global__ void flag_last_kernel(const float* __restrict__ raw, int F, int R, int S, float thr, const float* __restrict__ auto_thr,
+                                 int* __restrict__ count, int* __restrict__ rays) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)F * R) return;
+  if (thr < 0.f) thr = *auto_thr;
   const float sg = raw[(gid * S + (S - 1)) * 4 + 3];
   if (fabsf(sg) < thr) {
     const int f = (int)(gid / R);
@@ -201,9 +202,9 @@ int launch_tile_scan(const int* count, int F, int Sc, int* ts128, int* ts64, cud
   tile_scan_kernel<<<1, 256, 0, st>>>(count, F, Sc, ts128, ts64);
   return check_launch("tile_scan_kernel") ? 0 : 5;
 }
-int launch_flag_last(const float* raw, int F, int R, int S, float thr, int* count, int* rays, cudaStream_t st) {
+int launch_flag_last(const float* raw, int F, int R, int S, float thr, const float* auto_thr, int* count, int* rays, cudaStream_t st) {
   const long long n = (long long)F * R;
-  flag_last_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, F, R, S, thr, count, rays);
+  flag_last_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, F, R, S, thr, auto_thr, count, rays);
   return check_launch("flag_last_kernel") ? 0 : 5;
 }
 

@@ -308,6 +308,12 @@ __device__ __forceinline__ void split4_fp16f8(float x0, float x1, float x2, floa
   w5 = cvt_e5m2x2_f16x2(hmul2_u32(h01, kDnH2)) | (cvt_e5m2x2_f16x2(hmul2_u32(h23, kDnH2)) << 16);
 }
 
+#ifdef S2L_DBG_SATCOUNT
+// Debug builds (-DS2L_DBG_SATCOUNT, tools/check_fp16f8_domain.py): hidden activations that leave the validated fp16f8 domain
+// (|a| >= 4096: the scaled e4m3 residual saturates) are counted per translation unit; s2l_debug_sat_count_* read and clear.
+static __device__ unsigned long long g_sat_count = 0ull;
+#endif
+
 // One 32-column slice of an accumulator quarter -> next layer's A operand words (bias, ReLU, precision split), shared
 // by the single-CTA and CTA-pair kernels so both produce bit-identical operands.
 //   NPASS 3: o[0..15] bf16 hi pairs, o[16..31] bf16 lo pairs;   NPASS 1: o[0..15] bf16 pairs
@@ -321,6 +327,10 @@ __device__ __forceinline__ void convert_slice(const uint32_t (&v)[32], const flo
     const float2 t23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(bb.z, bb.w));
     const float x0 = fmaxf(t01.x, 0.f), x1 = fmaxf(t01.y, 0.f), x2 = fmaxf(t23.x, 0.f), x3 = fmaxf(t23.y, 0.f);
     if (NPASS == 2) {
+#ifdef S2L_DBG_SATCOUNT
+      const int nsat = (x0 >= kF8MaxAct) + (x1 >= kF8MaxAct) + (x2 >= kF8MaxAct) + (x3 >= kF8MaxAct);
+      if (nsat) atomicAdd(&g_sat_count, (unsigned long long)nsat);
+#endif
       split4_fp16f8(x0, x1, x2, x3, o[2 * j4], o[2 * j4 + 1], o[16 + j4], o[24 + j4]);
     } else {
       const uint32_t h0 = cvt_bf16x2(x0, x1), h1 = cvt_bf16x2(x2, x3);
@@ -524,7 +534,9 @@ __device__ __forceinline__ void reduce_tile(const TcArgs& a, int f, long long p0
     const float T_last = C * T_before;
     const float w = T_last * a_last;
     o[0] = fmaf(w, l0, acc0); o[1] = fmaf(w, l1, acc1); o[2] = fmaf(w, l2, acc2);
-    if (a.fix_thr > 0.f && fabsf(sig_last) < a.fix_thr) {
+    // fix_thr < 0: the model-dependent automatic threshold the pack kernels left in the blob (s2l_common.cuh META[3])
+    const float thr = a.fix_thr < 0.f ? reinterpret_cast<const float*>(a.blob + a.L.off_meta)[3] : a.fix_thr;
+    if (thr > 0.f && fabsf(sig_last) < thr) {
       a.carry[gray] = make_float4(T_last, acc0, acc1, acc2);
       const int slot = atomicAdd(a.next_count + f, 1);
       a.next_rays[(long long)f * s.R + slot] = ray;

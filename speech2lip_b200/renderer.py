@@ -71,7 +71,25 @@ class PackedWeights:
             _cabi.check(lib.s2l_pack_weights(arr, _ptr(self.blob), self.uv_dims, self.out_ch, _stream()),
                         "s2l_pack_weights")
         self._keepalive = tensors
+        self._meta = None
         return self
+
+    def meta(self):
+        """What the pack kernels recorded (one device->host read per pack, cached): {"max_abs_weight", "n_saturating_weights"
+        (tensor-core weights outside the fp16f8 domain |w| < 1024), "density_row_norm", "auto_fix_thr"}."""
+        if self._meta is None:
+            lib = _cabi.lib()
+            mw, ns, dn, ft = C.c_float(), C.c_int32(), C.c_float(), C.c_float()
+            with torch.cuda.device(self.blob.device):
+                _cabi.check(lib.s2l_blob_meta(_ptr(self.blob), C.byref(mw), C.byref(ns), C.byref(dn), C.byref(ft), _stream()), "s2l_blob_meta")
+            self._meta = {"max_abs_weight": mw.value, "n_saturating_weights": ns.value, "density_row_norm": dn.value,
+                          "auto_fix_thr": ft.value}
+        return self._meta
+
+    def fp16f8_weights_ok(self):
+        """True when every tensor-core weight lies in the validated fp16f8 domain (include/speech2lip_b200.h)."""
+        m = self.meta()
+        return m["n_saturating_weights"] == 0 and m["max_abs_weight"] < 1024.0
 
     @property
     def device(self):
@@ -282,11 +300,54 @@ class LipRenderer:
     """
 
     def __init__(self, weights, precision="bf16x3"):
-        if precision not in _cabi.PRECISIONS:
-            raise ValueError("precision must be one of %s" % sorted(_cabi.PRECISIONS))
+        if precision not in _cabi.PRECISIONS and precision != "auto":
+            raise ValueError("precision must be one of %s or 'auto'" % sorted(_cabi.PRECISIONS))
         self.w = weights
-        self.precision = precision
+        self.precision = precision            # "auto": fp16f8 inside its validated domain, else bf16x3
         self._scratch = None
+        self._act_max = None                  # largest hidden activation seen by probe_fp16f8_domain (None: never probed)
+
+    def _resolve_precision(self, name):
+        """fp16f8 is only used inside its validated domain (weights |w| < 1024 — recorded at pack time — and, once probed,
+        activations |a| < 4096): outside it the fp8 correction terms saturate silently, so the renderer switches to bf16x3
+        and says so (never silently)."""
+        if name not in ("fp16f8", "auto"):
+            return name
+        why = None
+        if not self.w.fp16f8_weights_ok():
+            m = self.w.meta()
+            why = "max |w| = %.3g, %d tensor-core weights >= 1024" % (m["max_abs_weight"], m["n_saturating_weights"])
+        elif self._act_max is not None and not self._act_max < 4096.0:
+            why = "probed hidden activations reach %.3g >= 4096" % self._act_max
+        if why is None:
+            return "fp16f8"
+        key = (id(self.w.blob), why)
+        if self.__dict__.get("_warned") != key:
+            self._warned = key
+            import warnings
+            warnings.warn("speech2lip_b200: model outside the validated fp16f8 domain (%s): using bf16x3 instead" % why, RuntimeWarning)
+        return "bf16x3"
+
+    def probe_fp16f8_domain(self, audio, index, pts):
+        """Runs the EXACT fp32 path (with saved activations) on sample points pts [N, uv_dims] of the first frame and records the
+        largest hidden activation; later fp16f8 / auto renders fall back to bf16x3 if it leaves the domain.  Returns
+        {"max_activation", "max_abs_weight", "ok"}."""
+        lib = _cabi.lib()
+        audio = _f32c(audio, "audio")
+        lat, _ = audio_encode(self.w, audio[:1], None, want_bias=False)
+        pts = _f32c(pts, "pts").reshape(-1, self.w.uv_dims)
+        x = torch.cat([pts, lat.expand(pts.shape[0], -1)], -1).contiguous()
+        N = x.shape[0]
+        out = torch.empty(N, self.w.out_ch, device=x.device)
+        acts = torch.empty(10, N, 256, device=x.device)
+        t = int(torch.as_tensor(index).reshape(-1)[0])
+        with torch.cuda.device(x.device):
+            _cabi.check(lib.s2l_rgb_forward_rows_train(_ptr(self.w.blob), _ptr(x), N, t, 1, _ptr(out), _ptr(acts), self.w.uv_dims,
+                                                       self.w.out_ch, _stream()), "s2l_rgb_forward_rows_train")
+        self._act_max = float(acts.abs().max().item())
+        m = self.w.meta()
+        return {"max_activation": self._act_max, "max_abs_weight": m["max_abs_weight"],
+                "ok": self.w.fp16f8_weights_ok() and self._act_max < 4096.0}
 
     def _scratch_for(self, geom, device, prec, want_aux):
         need = _cabi.lib().s2l_render_scratch_bytes(C.byref(geom), prec, 1 if want_aux else 0)
@@ -306,7 +367,7 @@ class LipRenderer:
         idx = torch.as_tensor(index).to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
         if idx.numel() != F:
             raise ValueError("index has %d entries for %d frames" % (idx.numel(), F))
-        prec = _cabi.PRECISIONS[precision or self.precision]
+        prec = _cabi.PRECISIONS[self._resolve_precision(precision or self.precision)]
         eps_pf = None
         if isinstance(eps_shift, torch.Tensor) and eps_shift.numel() > 1:      # one draw per frame (sync-window render)
             eps_pf = eps_shift.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
