@@ -3,7 +3,10 @@ library (-DS2L_DBG_SATCOUNT).   python tools/check_fp16f8_domain.py [weight-scal
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from speech2lip_b200.csrc import build as B
+import importlib.util
+_spec = importlib.util.spec_from_file_location("s2l_build", os.path.join(ROOT, "speech2lip_b200", "csrc", "build.py"))   # not via the package:
+B = importlib.util.module_from_spec(_spec)                                                                                # it binds the library
+_spec.loader.exec_module(B)
 so = os.path.join(ROOT, "tools", "dbg_satcount.so")
 if not os.path.exists(so):
     B.build(force=True, defines=("S2L_DBG_SATCOUNT",), out=so)
