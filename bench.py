@@ -729,9 +729,10 @@ def run_config3(a):
     barrier()
     gather_ms = g0.elapsed_time(g1)
     # ---- cross-rank checks
-    sums = out[:hi - lo].double().sum(dim=(1, 2, 3))
+    # per-frame checksum = integer sum of the fp32 bit patterns: exact and independent of the reduction order
+    sums = out[:hi - lo].view(torch.int32).to(torch.int64).sum(dim=(1, 2, 3))
     per = (T + world - 1) // world
-    pad = torch.zeros(per, dtype=torch.float64, device=dev)
+    pad = torch.zeros(per, dtype=torch.int64, device=dev)
     pad[:hi - lo] = sums
     if world > 1:
         parts = [torch.empty_like(pad) for _ in range(world)]
@@ -747,7 +748,7 @@ def run_config3(a):
     tmp = torch.empty(1, H, W, 3, device=dev)
     for pf in probes:                                         # every rank renders every probe itself
         render_block(pf, pf + 1, tmp)
-        bad += int(tmp.double().sum().item() != all_sums[pf].item())
+        bad += int(tmp.view(torch.int32).to(torch.int64).sum().item() != all_sums[pf].item())
         if world > 1:
             own = allf[pf].to(dev)
             bad += int(not torch.equal(R.frames_to_bgr8(tmp)[0], own))
