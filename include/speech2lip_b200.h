@@ -206,6 +206,16 @@ int32_t s2l_mlp_bwd_rows(const void* blob, const float* d_out, const float* acts
  *                   input layers.  No library GEMM is called.
  * geom: pts_mode = S2L_PTS_GRID_ENS4, uv_dims = 2, out_ch = 3, eps_shift / eps_per_frame as for s2l_render_frames.
  * workspace must hold s2l_train_workspace_bytes(geom) bytes and stay untouched between fwd and bwd (~9.3 KB per point). */
+/* AudioNet with gradients (tf_nerf.py:197-213 under autograd): the forward additionally saves its post-activation tensors
+ * (s2l_audio_train_save_floats(F) floats); the backward turns d_latent [F,64] into the gradients of the 12 AudioNet tensors
+ * (grads_host: HOST array of 12 DEVICE pointers, S2L_P_CONV0_W .. S2L_P_FC2_B order; written, not accumulated).  One CTA per
+ * frame + a frame reduction; scratch: s2l_audio_train_scratch_bytes(F). */
+size_t  s2l_audio_train_save_floats(int32_t n_frames);
+size_t  s2l_audio_train_scratch_bytes(int32_t n_frames);
+int32_t s2l_audio_train_fwd(const void* blob, const float* audio, int32_t transposed, float* latent, float* save, int32_t n_frames,
+                            void* stream);
+int32_t s2l_audio_train_bwd(const void* blob, const float* audio, int32_t transposed, const float* save, const float* d_latent,
+                            float* const* grads_host, void* scratch, int32_t n_frames, void* stream);
 size_t  s2l_train_workspace_bytes(const S2LGeom* geom);
 int32_t s2l_train_fwd(const void* blob, const S2LGeom* geom, const float* latent, const int64_t* frame_idx, float* rgb,
                       float* frame_bias, void* workspace, void* stream);

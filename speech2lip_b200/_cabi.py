@@ -59,6 +59,11 @@ SYMBOLS = {
     "s2l_rgb_forward_rows_train": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                                C.c_int32, C.c_int32, C.c_void_p]),
     "s2l_mlp_bwd_rows": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "s2l_audio_train_save_floats": (C.c_size_t, [C.c_int32]),
+    "s2l_audio_train_scratch_bytes": (C.c_size_t, [C.c_int32]),
+    "s2l_audio_train_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "s2l_audio_train_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p,
+                                        C.c_int32, C.c_void_p]),
     "s2l_train_workspace_bytes": (C.c_size_t, [C.POINTER(S2LGeom)]),
     "s2l_train_fwd": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "s2l_train_bwd": (C.c_int32, [C.c_void_p, C.POINTER(S2LGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -190,3 +190,48 @@ def render_lip_train(module, audio, index, H, W, eps_shift=None):
     sd = module._hot_params()
     params = [sd[n] for n in MLP_PARAM_NAMES]
     return FusedLipRender.apply(latent, index, eps_shift, int(H), int(W), module.packed_weights(), *params)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# AudioNet under autograd (tf_nerf.py:197-213): forward = the inference kernel + saved activations, backward = one CTA per
+# frame + a frame reduction (s2l_audio_train_fwd / s2l_audio_train_bwd).  No library convolution / GEMM.
+AUDIO_PARAM_NAMES = _cabi.PARAM_NAMES[:12]
+
+
+class AudioNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, audio, packed, *params):
+        lib = _cabi.lib()
+        audio = audio.contiguous().float()
+        if audio.dim() != 3 or audio.shape[1] * audio.shape[2] != 16 * 29:
+            raise ValueError("audio must be [B,16,29] or [B,29,16], got %s" % (tuple(audio.shape),))
+        F = audio.shape[0]
+        transposed = 1 if audio.shape[2] == 16 else 0
+        latent = torch.empty(F, 64, device=audio.device)
+        save = torch.empty(lib.s2l_audio_train_save_floats(F), device=audio.device)
+        with torch.cuda.device(audio.device):
+            _cabi.check(lib.s2l_audio_train_fwd(_ptr(packed.blob), _ptr(audio), transposed, _ptr(latent), _ptr(save), F, _stream()),
+                        "s2l_audio_train_fwd")
+        ctx.packed, ctx.transposed = packed, transposed
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(audio, save)
+        return latent
+
+    @staticmethod
+    def backward(ctx, d_latent):
+        lib = _cabi.lib()
+        audio, save = ctx.saved_tensors
+        F = audio.shape[0]
+        d_latent = d_latent.contiguous().float()
+        grads = [torch.empty(sh, device=audio.device) for sh in ctx.shapes]
+        scratch = torch.empty(max(lib.s2l_audio_train_scratch_bytes(F), 4), dtype=torch.uint8, device=audio.device)
+        arr = (C.c_void_p * 12)(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(audio.device):
+            _cabi.check(lib.s2l_audio_train_bwd(_ptr(ctx.packed.blob), _ptr(audio), ctx.transposed, _ptr(save), _ptr(d_latent), arr,
+                                                _ptr(scratch), F, _stream()), "s2l_audio_train_bwd")
+        return (None, None, *grads)
+
+
+def audio_merge_forward_train(module, audio):
+    sd = module._hot_params()
+    return AudioNetFn.apply(audio, module.packed_weights(), *[sd[n] for n in AUDIO_PARAM_NAMES])

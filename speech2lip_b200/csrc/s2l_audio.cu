@@ -10,6 +10,7 @@
 namespace s2l {
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.02f * x; }
+constexpr int kAudioSave = 256 + 128 + 128 + 64 + 64;      // x1 [32][8] | x2 [32][4] | x3 [64][2] | x4 [64] | x5 [64]
 
 // out[o][t] = b[o] + sum_c sum_j w[o][c][j] * in[c][2t-1+j], zero padded; in/out in shared memory
 template <int CIN, int COUT, int TIN>
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
                                                            float* __restrict__ latent, float* __restrict__ frame_bias,
                                                            const float* __restrict__ latent_in, long long latent_in_stride,
                                                            int n_frames, const int* __restrict__ gate_flag,
-                                                           const float* __restrict__ lat0) {
+                                                           const float* __restrict__ lat0, float* __restrict__ save = nullptr) {
   const float* A = reinterpret_cast<const float*>(blob + L.off_audio);
   const float* C = reinterpret_cast<const float*>(blob + L.off_const);
   const float* Fp = reinterpret_cast<const float*>(blob + L.off_fp32);
@@ -93,6 +94,12 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     const float v = acc + A[A_FC2_B + tid];
     lat[tid] = v;
     if (latent && !bcast) latent[(size_t)f * kLatent + tid] = v;
+  }
+  if (save) {      // training forward: the post-LeakyReLU activations the backward kernel needs (x1 | x2 | x3 | x4 | x5)
+    float* sv = save + (size_t)f * kAudioSave;
+    for (int i = tid; i < 256; i += 256) sv[i] = x1[i];
+    if (tid < 128) { sv[256 + tid] = x2[tid]; sv[384 + tid] = x3[tid]; }
+    if (tid < 64) { sv[512 + tid] = x4[tid]; sv[576 + tid] = x5[tid]; }
   }
   __syncthreads();
   if (bcast) {
@@ -257,4 +264,153 @@ extern "C" int32_t s2l_audio_merge_auto(const void* blob, const float* audio, in
   const int grid = (int)(n_rows < 148 * 4 ? n_rows : 148 * 4);
   audio_encode_kernel<<<grid, 256, 0, st>>>(b, blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, (int)n_rows, flag, lat0);
   return check_launch("audio_encode_kernel(auto)") ? 0 : 5;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// AudioNet backward (training): one CTA per frame walks the six layers backwards in shared memory and writes the frame's
+// weight-gradient contribution to a partial block; audio_bwd_reduce_kernel sums the frames (deterministic order).
+// Replaces autograd through tf_nerf.py:197-213 (4x Conv1d(k3,s2,p1) + LeakyReLU(0.02), Linear + LeakyReLU + Linear).
+namespace s2l {
+
+// pre-activation gradient from the post-activation value (LeakyReLU keeps the sign)
+__device__ __forceinline__ float dlrelu(float y, float g) { return y > 0.f ? g : 0.02f * g; }
+
+// conv layer backward: dp [COUT][TOUT] (gradient w.r.t. the pre-activation, in smem), in [CIN][TIN] (smem) ->
+// dW [COUT][CIN][3], db [COUT] (global partials) and, if d_in != null, d_in [CIN][TIN] (smem)
+template <int CIN, int COUT, int TIN>
+__device__ __forceinline__ void conv_k3s2_bwd(const float* __restrict__ w, const float* dp, const float* in, float* d_in,
+                                              float* __restrict__ dW, float* __restrict__ db, int tid, int nthreads) {
+  constexpr int TOUT = TIN / 2;
+  for (int idx = tid; idx < COUT * CIN * 3; idx += nthreads) {
+    const int o = idx / (CIN * 3), c = (idx / 3) % CIN, j = idx % 3;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < TOUT; ++t) {
+      const int ti = 2 * t - 1 + j;
+      if (ti >= 0 && ti < TIN) s = fmaf(dp[o * TOUT + t], in[c * TIN + ti], s);
+    }
+    dW[idx] = s;
+  }
+  for (int o = tid; o < COUT; o += nthreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < TOUT; ++t) s += dp[o * TOUT + t];
+    db[o] = s;
+  }
+  if (d_in) {
+    for (int idx = tid; idx < CIN * TIN; idx += nthreads) {
+      const int c = idx / TIN, ti = idx % TIN;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int tt = ti + 1 - j;                 // 2t - 1 + j = ti
+        if (tt >= 0 && (tt & 1) == 0 && tt / 2 < TOUT) {
+          const int t = tt / 2;
+          for (int o = 0; o < COUT; ++o) s = fmaf(w[(o * CIN + c) * 3 + j], dp[o * TOUT + t], s);
+        }
+      }
+      d_in[idx] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) audio_bwd_kernel(const uint8_t* __restrict__ blob, Layout L, const float* __restrict__ audio,
+                                                        int transposed, const float* __restrict__ save, const float* __restrict__ d_latent,
+                                                        float* __restrict__ partial) {
+  const float* A = reinterpret_cast<const float*>(blob + L.off_audio);
+  __shared__ float x0[kAudioFeat * kAudioWin], x1[256], x2[128], x3[128], x4[64], x5[64];
+  __shared__ float g5[64], g4[64], g3[128], g2[128], g1[256], gl[64];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const float* a = audio + (size_t)f * kAudioWin * kAudioFeat;
+  for (int i = tid; i < kAudioFeat * kAudioWin; i += 256) {
+    const int c = i / kAudioWin, t = i % kAudioWin;
+    x0[i] = transposed ? a[c * kAudioWin + t] : a[t * kAudioFeat + c];
+  }
+  const float* sv = save + (size_t)f * kAudioSave;
+  x1[tid] = sv[tid];
+  if (tid < 128) { x2[tid] = sv[256 + tid]; x3[tid] = sv[384 + tid]; }
+  if (tid < 64) { x4[tid] = sv[512 + tid]; x5[tid] = sv[576 + tid]; gl[tid] = d_latent[(size_t)f * kLatent + tid]; }
+  __syncthreads();
+  float* P = partial + (size_t)f * A_TOTAL;
+  // ---- encoder_fc1.2: lat = W2 x5 + b2
+  for (int i = tid; i < 64 * 64; i += 256) P[A_FC2_W + i] = gl[i >> 6] * x5[i & 63];
+  if (tid < 64) {
+    P[A_FC2_B + tid] = gl[tid];
+    float s = 0.f;
+    for (int o = 0; o < 64; ++o) s = fmaf(A[A_FC2_W + o * 64 + tid], gl[o], s);
+    g5[tid] = dlrelu(x5[tid], s);                       // gradient w.r.t. fc1.0's pre-activation
+  }
+  __syncthreads();
+  // ---- encoder_fc1.0: x5 = lrelu(W1 x4 + b1)
+  for (int i = tid; i < 64 * 64; i += 256) P[A_FC1_W + i] = g5[i >> 6] * x4[i & 63];
+  if (tid < 64) {
+    P[A_FC1_B + tid] = g5[tid];
+    float s = 0.f;
+    for (int o = 0; o < 64; ++o) s = fmaf(A[A_FC1_W + o * 64 + tid], g5[o], s);
+    g4[tid] = dlrelu(x4[tid], s);                       // conv3's pre-activation gradient [64][1]
+  }
+  __syncthreads();
+  conv_k3s2_bwd<64, 64, 2>(A + A_CONV3_W, g4, x3, g3, P + A_CONV3_W, P + A_CONV3_B, tid, 256);
+  __syncthreads();
+  if (tid < 128) g3[tid] = dlrelu(x3[tid], g3[tid]);
+  __syncthreads();
+  conv_k3s2_bwd<32, 64, 4>(A + A_CONV2_W, g3, x2, g2, P + A_CONV2_W, P + A_CONV2_B, tid, 256);
+  __syncthreads();
+  if (tid < 128) g2[tid] = dlrelu(x2[tid], g2[tid]);
+  __syncthreads();
+  conv_k3s2_bwd<32, 32, 8>(A + A_CONV1_W, g2, x1, g1, P + A_CONV1_W, P + A_CONV1_B, tid, 256);
+  __syncthreads();
+  g1[tid] = dlrelu(x1[tid], g1[tid]);
+  __syncthreads();
+  conv_k3s2_bwd<29, 32, 16>(A + A_CONV0_W, g1, x0, nullptr, P + A_CONV0_W, P + A_CONV0_B, tid, 256);
+}
+
+struct AudioGradPtrs {
+  float* g[12];        // encoder_conv.{0,2,4,6}.{weight,bias}, encoder_fc1.{0,2}.{weight,bias} (S2L_P_* order)
+};
+__global__ void __launch_bounds__(256) audio_bwd_reduce_kernel(const float* __restrict__ partial, int F, AudioGradPtrs G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A_TOTAL) return;
+  float s = 0.f;
+  for (int f = 0; f < F; ++f) s += partial[(size_t)f * A_TOTAL + i];
+  const int off[13] = {A_CONV0_W, A_CONV0_B, A_CONV1_W, A_CONV1_B, A_CONV2_W, A_CONV2_B, A_CONV3_W,
+                       A_CONV3_B, A_FC1_W,   A_FC1_B,   A_FC2_W,   A_FC2_B,   A_TOTAL};
+  int t = 0;
+  while (i >= off[t + 1]) ++t;
+  G.g[t][i - off[t]] = s;
+}
+
+}  // namespace s2l
+
+extern "C" size_t s2l_audio_train_save_floats(int32_t n_frames) { return (size_t)(n_frames > 0 ? n_frames : 0) * s2l::kAudioSave; }
+extern "C" size_t s2l_audio_train_scratch_bytes(int32_t n_frames) { return (size_t)(n_frames > 0 ? n_frames : 0) * s2l::A_TOTAL * sizeof(float); }
+
+extern "C" int32_t s2l_audio_train_fwd(const void* blob, const float* audio, int32_t transposed, float* latent, float* save,
+                                       int32_t n_frames, void* stream) {
+  if (!blob || (n_frames > 0 && (!audio || !latent || !save))) { set_error("s2l_audio_train_fwd: null argument"); return 1; }
+  if (n_frames < 0) { set_error("s2l_audio_train_fwd: negative n_frames"); return 2; }
+  if (n_frames == 0) return 0;
+  audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, n_frames, nullptr,
+      nullptr, save);
+  return check_launch("audio_encode_kernel(train)") ? 0 : 5;
+}
+
+extern "C" int32_t s2l_audio_train_bwd(const void* blob, const float* audio, int32_t transposed, const float* save,
+                                       const float* d_latent, float* const* grads_host, void* scratch, int32_t n_frames, void* stream) {
+  if (!blob || !grads_host || (n_frames > 0 && (!audio || !save || !d_latent || !scratch))) { set_error("s2l_audio_train_bwd: null argument"); return 1; }
+  if (n_frames < 0) { set_error("s2l_audio_train_bwd: negative n_frames"); return 2; }
+  s2l::AudioGradPtrs G{};
+  for (int i = 0; i < 12; ++i) {
+    if (!grads_host[i]) { set_error("s2l_audio_train_bwd: gradient buffer %d is null", i); return 3; }
+    G.g[i] = grads_host[i];
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n_frames > 0) {
+    s2l::audio_bwd_kernel<<<n_frames, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed, save, d_latent,
+                                                    reinterpret_cast<float*>(scratch));
+    if (!check_launch("audio_bwd_kernel")) return 5;
+  }
+  s2l::audio_bwd_reduce_kernel<<<(s2l::A_TOTAL + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), n_frames, G);
+  return check_launch("audio_bwd_reduce_kernel") ? 0 : 5;
 }

@@ -222,11 +222,14 @@ class TalkingFace(nn.Module):
     def audio_merge_forward(self, audio):
         """tf_nerf.py:197-213.  audio: [B,16,29] or [B,29,16] -> [B,64]."""
         if self._needs_grad(audio):
-            # training: AudioNet is 67 k MAC per frame — its forward/backward stay on autograd (SURVEY §7 step 8);
-            # the result feeds the fused MLP's autograd.Function through the latent columns of rgb_forward's input
+            if audio.is_cuda and not audio.requires_grad:
+                # training: the inference kernel with saved activations + a hand-written backward (one CTA per frame); the
+                # latent feeds the fused MLP's autograd.Function (rows contract or render_lip_train)
+                from .autograd import audio_merge_forward_train
+                return audio_merge_forward_train(self, audio)
+            # a caller differentiating w.r.t. the audio window itself: plain autograd (Conv1d(k3,s2,p1) as unfold + matmul)
             x = audio if audio.shape[2] == 16 else audio.permute(0, 2, 1)
             for i in (0, 2, 4, 6):
-                # Conv1d(k3,s2,p1) as unfold + matmul: true-fp32 GEMMs in both directions (cuDNN would pick TF32 by default)
                 conv = self.encoder_conv[i]
                 cols = F.pad(x, (1, 1)).unfold(2, 3, 2)                                  # [B,C,T/2,3]
                 cols = cols.permute(0, 2, 1, 3).reshape(x.shape[0], cols.shape[2], -1)   # [B,T/2,C*3]

@@ -315,3 +315,33 @@ def test_sync_window_render_with_gradients(S):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0 for p in m._hot_params().values())
     # frames 3 and 4 share the clamped time index 99 but not their audio windows
     assert not torch.equal(got[3], got[4])
+
+
+@pytest.mark.parametrize("layout", ["16x29", "29x16"])
+def test_audio_net_backward_kernel_vs_oracle_autograd(S, layout):
+    """AudioNet's hand-written backward (one CTA per frame + frame reduction) against torch autograd of the oracle's
+    audio_merge_forward on CPU: fp32 on both sides, 1e-5 relative per tensor; both input orientations (tf_nerf.py:203-207);
+    the tiled training call pattern (training.py:171: one window per batch item) included through the module."""
+    import json
+    cfg = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "may_cfg.json")))
+    sd_np = synth.make_state_dict(0, "kaiming", 2, 3)
+    m = S.TalkingFace(device=dev(), cfg=cfg).to(dev()).train()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()}, strict=False)
+    F = 5
+    audio = torch.from_numpy(synth.make_audio(F, seed=81))
+    if layout == "29x16":
+        audio = audio.permute(0, 2, 1).contiguous()
+    g = torch.randn(F, 64, generator=torch.Generator().manual_seed(9))
+    osd = {k: v.clone().requires_grad_(True) for k, v in O.to_torch_sd(sd_np).items()}
+    want = O.audio_merge_forward(osd, audio)
+    (want * g).sum().backward()
+    got = m.audio_merge_forward(audio.to(dev()))
+    assert got.grad_fn is not None and type(got.grad_fn).__name__.startswith("AudioNetFn")
+    (got * g.to(dev())).sum().backward()
+    e_fwd = (got.detach().cpu() - want.detach()).abs().max().item()
+    worst = 0.0
+    for k, p in m._hot_params().items():
+        if k.startswith("encoder_"):
+            worst = max(worst, ((p.grad.cpu() - osd[k].grad).norm() / (osd[k].grad.norm() + 1e-30)).item())
+    print("AudioNet backward kernel (%s): forward %.2e, worst relative gradient error %.2e" % (layout, e_fwd, worst))
+    assert e_fwd < 1e-5 and worst < 1e-5
