@@ -563,7 +563,9 @@ __device__ __forceinline__ void reducer_role(const TcArgs& a, long long n_tiles,
     const int buf = (int)(it & 1);
     int f; long long p0, Pf;
     tile_locate<TC_TM>(a.src, a.tiles_per_frame, n_tiles, tile, fcur, f, p0, Pf);
-    mbar_wait_wd(&raw_full[buf], (uint32_t)((it >> 1) & 1), 900 + buf);
+    // back-off while waiting: this warp idles for a whole tile time and shares its scheduler with two epilogue warps and a
+    // PE producer — a tight poll loop here takes issue slots from the critical path
+    mbar_wait_wd<true>(&raw_full[buf], (uint32_t)((it >> 1) & 1), 900 + buf);
     reduce_tile(a, f, p0, Pf, rawbuf + buf * TC_TM, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(&raw_empty[buf]);
