@@ -103,6 +103,8 @@ static PointSrc make_src(const S2LGeom& g, const float* pts, const float* ro, co
   s.eps_pf = (g.pts_mode == S2L_PTS_GRID_ENS4) ? g.eps_per_frame : nullptr;
   s.P = points_per_frame(g);
   s.R = g.height * g.width;
+  s.step_w = g.width > 1 ? 1.0f / (float)(g.width - 1) : 0.f;
+  s.step_h = g.height > 1 ? 1.0f / (float)(g.height - 1) : 0.f;
   s.s0 = 0;
   s.Sc = s.S;
   s.pts = pts;

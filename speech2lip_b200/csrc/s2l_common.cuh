@@ -216,10 +216,12 @@ __device__ __forceinline__ bool elect_one() {
 // Both back ends contract the second form into ONE fused multiply-add (nvcc's default -fmad=true on CUDA, the
 // vectorised fmadd on CPU), i.e. round(1 - step*k) with a single rounding — two roundings differ by 1 ulp in ~9 % of the
 // coordinates at W = 256, which the 2^9 positional-encoding frequency turns into ~1e-4 at the output.
-__device__ __forceinline__ float linspace01(int i, int n) {
+__device__ __forceinline__ float linspace01(int i, int n, float step) {      // step = 1.0f / (float)(n - 1), IEEE fp32 division
   if (n == 1) return 0.f;
-  const float step = __fdiv_rn(1.0f, (float)(n - 1));
   return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
+}
+__device__ __forceinline__ float linspace01(int i, int n) {
+  return linspace01(i, n, n > 1 ? __fdiv_rn(1.0f, (float)(n - 1)) : 0.f);
 }
 // density2outputs pieces (rendering.py:43-58), shared by composite_kernel, the fused reducer warp and the fp32
 // re-evaluation kernel so that all three round identically

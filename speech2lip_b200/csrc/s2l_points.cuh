@@ -16,6 +16,8 @@ struct PointSrc {
   long long P;          // point evaluations per frame (RAYS: R * Sc)
   const float* pts;     // EXPLICIT: [F*P, uv_dims] (row stride pts_stride floats; 0 = uv_dims)
   int pts_stride;
+  float step_w, step_h; // GRID*: 1.0f / (W - 1), 1.0f / (H - 1) (fp32 division on the host = ATen's linspace step; saves a division
+                        // routine per coordinate in the kernels)
   const float* rays_o;  // RAYS
   const float* rays_d;
   const float* z;
@@ -57,27 +59,28 @@ __device__ __forceinline__ int ray_of_point(const PointSrc& s, int f, long long 
 // Coordinates of point p (0 <= p < P) of frame f.  Arithmetic mirrors the reference op by op
 // (separate fp32 roundings, no FMA contraction) so that inputs to the PE are bit-identical to what
 // PyTorch computes on the GPU.
+// One tap of the 4-tap local ensemble (training.py:195-209): taps ordered (vx,vy) = (-1,-1),(-1,1),(1,-1),(1,1);
+// coord += v*r + eps (the python scalar v*r is rounded to fp32 before the add), clamp to [0,1].  (u0, v0) = the pixel centre.
+__device__ __forceinline__ void ens4_tap(const PointSrc& s, float u0, float v0, float eps, int tap, float& u, float& v) {
+  const float rx = (float)(0.5 / (double)s.W), ry = (float)(0.5 / (double)s.H);      // |v*r| rounded to fp32 (exact sign symmetry)
+  u = fminf(fmaxf(__fadd_rn(u0, __fadd_rn((tap & 2) ? rx : -rx, eps)), 0.f), 1.f);
+  v = fminf(fmaxf(__fadd_rn(v0, __fadd_rn((tap & 1) ? ry : -ry, eps)), 0.f), 1.f);
+}
+__device__ __forceinline__ void grid_centre(const PointSrc& s, unsigned pix, float& u0, float& v0) {
+  const unsigned py = pix / (unsigned)s.W, px = pix - py * (unsigned)s.W;               // pixel indices fit 32 bits
+  u0 = linspace01((int)px, s.W, s.step_w);
+  v0 = linspace01((int)py, s.H, s.step_h);
+}
+
 __device__ __forceinline__ void gen_point(const PointSrc& s, int f, long long p, float x[3]) {
   x[0] = x[1] = x[2] = 0.f;
   if (s.mode == S2L_PTS_GRID) {
     // get_coords, rendering.py:18-22: coords[y*W+x] = (linspace(0,1,W)[x], linspace(0,1,H)[y])
-    const int px = (int)(p % s.W), py = (int)(p / s.W);
-    x[0] = linspace01(px, s.W);
-    x[1] = linspace01(py, s.H);
+    grid_centre(s, (unsigned)p, x[0], x[1]);
   } else if (s.mode == S2L_PTS_GRID_ENS4) {
-    // training.py:195-209: taps ordered (vx,vy) = (-1,-1),(-1,1),(1,-1),(1,1);
-    // coord += v*r + eps (the python scalar v*r is rounded to fp32 before the add), clamp to [0,1]
-    const long long pix = p >> 2;
-    const int tap = (int)(p & 3);
-    const int px = (int)(pix % s.W), py = (int)(pix / s.W);
-    const float vx = (tap & 2) ? 1.f : -1.f, vy = (tap & 1) ? 1.f : -1.f;
-    const float rx = (float)((double)vx * (0.5 / (double)s.W));
-    const float ry = (float)((double)vy * (0.5 / (double)s.H));
-    const float eps = s.eps_pf ? s.eps_pf[f] : s.eps;
-    const float u = __fadd_rn(linspace01(px, s.W), __fadd_rn(rx, eps));
-    const float v = __fadd_rn(linspace01(py, s.H), __fadd_rn(ry, eps));
-    x[0] = fminf(fmaxf(u, 0.f), 1.f);
-    x[1] = fminf(fmaxf(v, 0.f), 1.f);
+    float u0, v0;
+    grid_centre(s, (unsigned)(p >> 2), u0, v0);
+    ens4_tap(s, u0, v0, s.eps_pf ? s.eps_pf[f] : s.eps, (int)(p & 3), x[0], x[1]);
   } else if (s.mode == S2L_PTS_RAYS) {
     // pts = rays_o[:,None,:] + rays_d[:,None,:] * z[...,None]   (NeRF sample placement)
     const long long ray = ray_of_point(s, f, p);
@@ -105,6 +108,12 @@ __device__ __forceinline__ void tile_locate(const PointSrc& s, long long tiles_p
     f = fcur;
     p0 = (tile - s.tile_start[f]) * TMX;
     Pf = (long long)s.list_count[f] * s.Sc;
+  } else if (n_tiles < 0x7fffffffll) {          // 32-bit division (the 64-bit one is a ~100-instruction routine)
+    const unsigned t32 = (unsigned)tile, tpf = (unsigned)tiles_per_frame;
+    const unsigned q = t32 / tpf;
+    f = (int)q;
+    p0 = (long long)(t32 - q * tpf) * TMX;
+    Pf = s.P;
   } else {
     f = (int)(tile / tiles_per_frame);
     p0 = (tile % tiles_per_frame) * TMX;
@@ -112,10 +121,28 @@ __device__ __forceinline__ void tile_locate(const PointSrc& s, long long tiles_p
   }
 }
 
+// The four blend weights of a pixel (training.py:237-249): area of every tap's rectangle against the pixel centre (+1e-9),
+// normalised by their sum, and used SWAPPED (tap t is weighted with the area of tap 3 - t).
+__device__ __forceinline__ void ens4_weights(const PointSrc& s, int f, unsigned pix, float (&w)[4]);
+
 // 4-tap area weight of training.py:237-245 for tap `tap` of the pixel whose centre is (u0,v0) and whose
 // jittered taps are c[t]; returns areas[t]+1e-9 for all taps.
 __device__ __forceinline__ float ens4_area(float cu, float cv, float u0, float v0) {
   return __fadd_rn(fabsf(__fmul_rn(__fsub_rn(cu, u0), __fsub_rn(cv, v0))), 1e-9f);
+}
+__device__ __forceinline__ void ens4_weights(const PointSrc& s, int f, unsigned pix, float (&w)[4]) {
+  float u0, v0, area[4];
+  grid_centre(s, pix, u0, v0);
+  const float eps = s.eps_pf ? s.eps_pf[f] : s.eps;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float u, v;
+    ens4_tap(s, u0, v0, eps, t, u, v);
+    area[t] = ens4_area(u, v, u0, v0);
+  }
+  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) w[t] = __fdiv_rn(area[3 - t], tot);
 }
 #endif
 

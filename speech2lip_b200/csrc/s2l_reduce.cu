@@ -15,22 +15,14 @@ __global__ void ensemble4_blend_kernel(const float* __restrict__ raw, PointSrc s
   if (gid >= npix * n_frames) return;
   const int f = (int)(gid / npix);
   const long long pix = gid % npix;
-  const int px = (int)(pix % src.W), py = (int)(pix / src.W);
-  const float u0 = linspace01(px, src.W), v0 = linspace01(py, src.H);
-  float area[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    float x[3];
-    gen_point(src, f, pix * 4 + t, x);
-    area[t] = ens4_area(x[0], x[1], u0, v0);
-  }
   // tot_area = stack(areas).sum(0); then areas 0<->3, 1<->2 are swapped (training.py:243-245)
-  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+  float wt[4];
+  ens4_weights(src, f, (unsigned)pix, wt);
   const float* r = raw + (gid * 4) * out_ch;
   float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float w = __fdiv_rn(area[3 - t], tot);
+    const float w = wt[t];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       if (c < out_ch) acc[c] = __fadd_rn(acc[c], __fmul_rn(r[t * out_ch + c], w));
@@ -239,6 +231,8 @@ extern "C" int32_t s2l_ensemble4_blend(const float* raw, const S2LGeom* g, float
   src.eps = g->eps_shift;
   src.eps_pf = g->eps_per_frame;
   src.P = (long long)g->height * g->width * 4;
+  src.step_w = g->width > 1 ? 1.0f / (float)(g->width - 1) : 0.f;
+  src.step_h = g->height > 1 ? 1.0f / (float)(g->height - 1) : 0.f;
   const long long n = (long long)g->height * g->width * g->n_frames;
   if (n == 0) return 0;
   ensemble4_blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

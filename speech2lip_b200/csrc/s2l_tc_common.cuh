@@ -209,12 +209,11 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 // (~30 s of SM clocks; a launch lasts ~0.1 s): a kernel slowed 100x by compute-sanitizer, or time-sliced against another
 // process, must not be mistaken for a deadlock.
 constexpr long long kWatchdogCycles = 60000000000ll;
-template <bool BACKOFF = false>
-__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
-#ifdef S2L_DBG_SUSPEND       // experiment: let the hardware park the warp (up to ~20 us) instead of polling
-  if (mbar_try_wait_hint(bar, parity, 20000u)) return;
-#endif
-  if (mbar_try_wait(bar, parity)) return;
+// The polling loop is a real function call, NOT inlined: these kernels are ~190 KB of straight-line code against a
+// ~128 KB instruction cache (ncu: 15 % of the stall samples are instruction-fetch stalls), and an inlined copy of this loop
+// with its printf at each of ~40 wait sites is pure footprint.  The fast path (barrier already complete) stays inline.
+template <bool BACKOFF>
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (BACKOFF) __nanosleep(128);     // roles that run ahead (producers) must not steal issue slots while they wait
@@ -224,6 +223,14 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int
       __trap();
     }
   }
+}
+template <bool BACKOFF = false>
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef S2L_DBG_SUSPEND       // experiment: let the hardware park the warp (up to ~20 us) instead of polling
+  if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+#endif
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow<BACKOFF>(bar, parity, tag);
 }
 
 // Same bounded wait without the printf (a call inside the MMA warp's loop would force every loop-carried value
@@ -362,7 +369,9 @@ __device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long lo
     gen_point(src, f, p, x);
 #pragma unroll
     for (int d = 0; d < UVD; ++d) e[d] = x[d];
-#pragma unroll
+    // rolled over the 10 frequencies (the accurate sincosf inlines to ~50 instructions; 60 copies of it were a quarter of the
+    // kernel's code): e[] then lives in local memory, which this role — one tile ahead of the MMAs — can afford
+#pragma unroll 1
     for (int k = 0; k < kMultires; ++k) {
 #pragma unroll
       for (int d = 0; d < UVD; ++d) {
@@ -440,6 +449,13 @@ __device__ __forceinline__ void pe_write_row(const PointSrc& src, int f, long lo
 // On the final chunk rays whose last-sample density is within fix_thr of zero are listed for the fp32 re-evaluation
 // (rendering.py:44 gives the last sample delta = 1e10: alpha_last is a step function of sign(sigma_last), so a
 // tensor-core rounding error there flips the pixel; the exact kernel redoes those few rays, s2l_mlp_fp32.cu).
+// The reducer shares a warp scheduler with two epilogue warps that sit on the MMA critical path, so its per-point math is the
+// hardware-approximate kind (ex2.approx / rcp: a few instructions instead of ~20 for expf / IEEE division).  Their relative
+// error (2^-21) is a few 1e-7 on alpha and sigmoid — three orders of magnitude inside the 1e-3 parity bar; composite_kernel
+// (the unfused path, weights / depth outputs) keeps the exact functions.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float alpha_fast(float sigma, float dist) { return 1.f - __expf(-(fmaxf(sigma, 0.f) * dist)); }
+
 __device__ __forceinline__ void reduce_tile(const TcArgs& a, int f, long long p0, long long Pf, const float4* rawbuf, int lane) {
   const PointSrc& s = a.src;
   const long long p = p0 + 4 * lane;
@@ -447,41 +463,36 @@ __device__ __forceinline__ void reduce_tile(const TcArgs& a, int f, long long p0
   if (a.epi_mode == EPI_ENS4) {
     if (!valid) return;
     const long long pix = p >> 2;
-    const int px = (int)(pix % s.W), py = (int)(pix / s.W);
-    const float u0 = linspace01(px, s.W), v0 = linspace01(py, s.H);
-    float area[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float x[3];
-      gen_point(s, f, p + t, x);
-      area[t] = ens4_area(x[0], x[1], u0, v0);
-    }
-    const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+    float wt[4];
+    ens4_weights(s, f, (unsigned)pix, wt);             // areas 0<->3, 1<->2 swapped (training.py:243-245)
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const float w = __fdiv_rn(area[3 - t], tot);       // areas 0<->3, 1<->2 swapped (training.py:243-245)
       const float4 v = rawbuf[4 * lane + t];
-      acc[0] = __fadd_rn(acc[0], __fmul_rn(v.x, w));
-      acc[1] = __fadd_rn(acc[1], __fmul_rn(v.y, w));
-      acc[2] = __fadd_rn(acc[2], __fmul_rn(v.z, w));
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(v.x, wt[t]));
+      acc[1] = __fadd_rn(acc[1], __fmul_rn(v.y, wt[t]));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(v.z, wt[t]));
     }
     float* o = a.rgb + ((long long)f * s.H * s.W + pix) * 3;
     o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
     return;
   }
-  // ---- EPI_COMPOSITE
+  // ---- EPI_COMPOSITE  (Sc is a power of two: shifts and masks, 32-bit indices — this warp shares its issue slots with
+  //      two epilogue warps, every instruction here is taken from them)
   const int L = s.Sc >> 2;                 // lanes per ray: 1, 2, 4, ..., 32
   const int sub = lane & (L - 1);
+  const int lg = 31 - __clz(s.Sc);
   float Tl = 1.f, A0 = 0.f, A1 = 0.f, A2 = 0.f;
   float a_last = 0.f, T_before = 1.f, sig_last = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
   float Tin = 1.f, B0 = 0.f, B1 = 0.f, B2 = 0.f;
   int ray = 0;
   bool has_last = false;
   if (valid) {
-    ray = ray_of_point(s, f, p);
+    const int p32 = (int)p;
+    const int slot = p32 >> lg;
+    ray = s.list_rays ? s.list_rays[(long long)f * s.R + slot] : slot;
     const long long gray = (long long)f * s.R + ray;
-    const int smp = s.s0 + (int)(p % s.Sc);
+    const int smp = s.s0 + (p32 & (s.Sc - 1));
     const float nrm = ray_norm(s.rays_d + (s.rays_shared ? (long long)ray : gray) * 3);
     const float* zr = s.z_per_ray ? s.z + gray * s.S : s.z;
     if (s.s0 > 0) {
@@ -501,8 +512,8 @@ __device__ __forceinline__ void reduce_tile(const TcArgs& a, int f, long long p0
       } else {
         dist = __fmul_rn(1e10f, nrm);
       }
-      const float alpha = alpha_of(v.w, dist);
-      const float c0 = sigmoidf_acc(v.x), c1 = sigmoidf_acc(v.y), c2 = sigmoidf_acc(v.z);
+      const float alpha = alpha_fast(v.w, dist);
+      const float c0 = sigmoid_fast(v.x), c1 = sigmoid_fast(v.y), c2 = sigmoid_fast(v.z);
       if (has_last && i == 3) {
         a_last = alpha; T_before = Tl; sig_last = v.w; l0 = c0; l1 = c1; l2 = c2;
       } else {
@@ -566,7 +577,9 @@ __device__ __forceinline__ void reducer_role(const TcArgs& a, long long n_tiles,
     // back-off while waiting: this warp idles for a whole tile time and shares its scheduler with two epilogue warps and a
     // PE producer — a tight poll loop here takes issue slots from the critical path
     mbar_wait_wd<true>(&raw_full[buf], (uint32_t)((it >> 1) & 1), 900 + buf);
+#ifndef S2L_DBG_NOREDUCE      // experiment: the hand-off protocol alone (no per-pixel work; results are garbage, timing only)
     reduce_tile(a, f, p0, Pf, rawbuf + buf * TC_TM, lane);
+#endif
     __syncwarp();
     if (lane == 0) mbar_arrive(&raw_empty[buf]);
   }

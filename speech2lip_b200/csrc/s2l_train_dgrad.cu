@@ -205,17 +205,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
         // weight of this tap in the blend: area of the OPPOSITE tap / total area (training.py:237-249)
         const long long pix = p >> 2;
         const int tap = (int)(p & 3);
-        const int px = (int)(pix % a.src.W), py = (int)(pix / a.src.W);
-        const float u0 = linspace01(px, a.src.W), v0 = linspace01(py, a.src.H);
-        float area[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float x[3];
-          gen_point(a.src, f, pix * 4 + t, x);
-          area[t] = ens4_area(x[0], x[1], u0, v0);
-        }
-        const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
-        const float w = __fdiv_rn(area[3 - tap], tot);
+        float wt[4];
+        ens4_weights(a.src, f, (unsigned)pix, wt);
+        const float w = wt[tap];
         const float* g = a.d_rgb + ((long long)f * npix + pix) * 3;
         d[0] = w * g[0]; d[1] = w * g[1]; d[2] = w * g[2];
       }

@@ -231,6 +231,8 @@ static PointSrc train_src(const S2LGeom& g) {
   s.eps_pf = g.eps_per_frame;
   s.P = (long long)g.height * g.width * 4;
   s.R = g.height * g.width;
+  s.step_w = g.width > 1 ? 1.0f / (float)(g.width - 1) : 0.f;
+  s.step_h = g.height > 1 ? 1.0f / (float)(g.height - 1) : 0.f;
   return s;
 }
 

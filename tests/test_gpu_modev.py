@@ -87,7 +87,8 @@ def oracle_rays(sdv, audio, index, ro, rd, z, sel):
 @pytest.mark.parametrize("Sn", [4, 8, 16, 32, 64, 128])
 def test_fused_compositing_equals_unfused(S, precision, Sn):
     """The reducer warp's compositing (fused epilogue, no raw tensor) against the same kernel's raw outputs composited by
-    composite_kernel, re-evaluation off in both: only the summation order differs (<= 2e-6).  Ragged ray counts, several
+    composite_kernel, re-evaluation off in both: the summation order and the reducer's hardware-approximate exp / reciprocal
+    (2^-21 relative) differ (<= 1e-5).  Ragged ray counts, several
     frames, both schedules' tail handling (H*W*S not a multiple of 128)."""
     H, W, F = 9, 13, 3
     w = packed(S)
@@ -101,7 +102,7 @@ def test_fused_compositing_equals_unfused(S, precision, Sn):
     unfused, weights, depth = r.render_frames(audio, idx, H, W, return_aux=True, **kw)
     e = (fused - unfused).abs().max().item()
     print("fused vs unfused S=%d %s: %.3e" % (Sn, precision, e))
-    assert e < 2e-6
+    assert e < 1e-5
     # per-ray z / per-frame rays forms hit the same fused code path bit for bit
     again = r.render_frames(audio, idx, H, W, mode="volumetric", rays_o=ro.repeat(F, 1).to(dev()), rays_d=rd.repeat(F, 1).to(dev()),
                             z_vals=z.expand(F * H * W, Sn).contiguous().to(dev()), fix_thr=-1.0)
@@ -189,7 +190,7 @@ def test_sample_chunks_without_termination_equal_one_launch(S, precision, chunks
     assert (cnt["alive"] == H * W).all()
     e = (one - many).abs().max().item()
     print("chunks=%d %s: %.3e" % (chunks, precision, e))
-    assert e < 3e-6
+    assert e < 1e-5
 
 
 @pytest.mark.parametrize("scale", [1.0, 30.0, 300.0])

@@ -196,7 +196,7 @@ def test_volumetric_vs_golden(S, golden, kind, shape, precision):
                            rays_o=torch.from_numpy(g["rays_o"]).to(dev()), rays_d=torch.from_numpy(g["rays_d"]).to(dev()),
                            z_vals=z.expand(H * W, Sn).contiguous())
     # (without weights/depth the tensor-core precisions composite inside the MLP kernel: same arithmetic, other summation order)
-    assert torch.equal(rgb2, rgb) if precision == "fp32" else (rgb2 - rgb).abs().max().item() < 2e-6
+    assert torch.equal(rgb2, rgb) if precision == "fp32" else (rgb2 - rgb).abs().max().item() < 1e-5
 
 
 # ------------------------------------------------------------------------------------------ oracle at seeded mid sizes
