@@ -142,6 +142,8 @@ class FusedLipRender(torch.autograd.Function):
         lib = _cabi.lib()
         if packed.uv_dims != 2 or packed.out_ch != 3:
             raise ValueError("the training render is the live 4-tap mode (uv_dims=2, output_ch=3)")
+        if not latent.is_cuda:
+            raise RuntimeError("speech2lip_b200: render_lip_train needs CUDA tensors (the hot path has no CPU fallback)")
         latent = latent.contiguous().float()
         F = latent.shape[0]
         dev = latent.device
@@ -202,6 +204,8 @@ class AudioNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, audio, packed, *params):
         lib = _cabi.lib()
+        if not audio.is_cuda:
+            raise RuntimeError("speech2lip_b200: AudioNet needs CUDA tensors (the hot path has no CPU fallback)")
         audio = audio.contiguous().float()
         if audio.dim() != 3 or audio.shape[1] * audio.shape[2] != 16 * 29:
             raise ValueError("audio must be [B,16,29] or [B,29,16], got %s" % (tuple(audio.shape),))

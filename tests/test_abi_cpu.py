@@ -192,3 +192,58 @@ def test_drop_in_helper_entry_points_report_errors():
     assert lib.s2l_rows_differ(None, 4, 8, 0, 8, None, None) == 1 and b"null" in lib.s2l_last_error()
     assert lib.s2l_rows_differ(C.c_void_p(16), 4, 8, 4, 8, C.c_void_p(16), None) == 2 and b"shape" in lib.s2l_last_error()
     assert lib.s2l_tc_schedule(0) in (1, 2, 3)
+
+
+def test_round2_entry_points_validate_arguments_before_touching_the_device():
+    """The ABI v2 additions (render options, device-gated drop-in calls, training path, AudioNet backward, blob meta) reject
+    bad arguments with a message instead of launching."""
+    lib = _cabi.lib()
+    p16 = C.c_void_p(16)
+    g = _cabi.S2LGeom(n_frames=1, height=4, width=4, n_samples=6, pts_mode=_cabi.PTS_RAYS, uv_dims=3, out_ch=4, sample_chunks=2, term_thr=1e-4)
+    # 6 samples cannot be cut into chunks of 4..128 samples: refused, not silently rendered in one launch
+    assert lib.s2l_render_frames(p16, C.byref(g), p16, None, p16, p16, p16, p16, None, None, p16, _cabi.PREC_FP16F8, None) == 2
+    assert b"sample_chunks" in lib.s2l_last_error()
+    g.sample_chunks = 0
+    assert lib.s2l_render_frames(p16, C.byref(g), p16, None, p16, p16, p16, p16, None, None, p16, 9, None) == 2 and b"precision" in lib.s2l_last_error()
+    # scratch: the fused volumetric render needs no raw tensor, the unfused one does
+    g2 = _cabi.S2LGeom(n_frames=8, height=256, width=256, n_samples=64, pts_mode=_cabi.PTS_RAYS, uv_dims=3, out_ch=4)
+    fused = lib.s2l_render_scratch_bytes(C.byref(g2), _cabi.PREC_FP16F8, 0)
+    unfused = lib.s2l_render_scratch_bytes(C.byref(g2), _cabi.PREC_FP16F8, 1)
+    exact = lib.s2l_render_scratch_bytes(C.byref(g2), _cabi.PREC_FP32, 0)
+    assert fused < 32 << 20 and unfused > 8 * 256 * 256 * 64 * 16 and exact > 8 * 256 * 256 * 64 * 16
+    assert lib.s2l_render_counts_offset(C.byref(g2)) == 8 * 4 * 256 * 4
+    assert lib.s2l_rgb_forward_auto(None, None, 4, None, None, 2, 3, 1, None, None) == 1 and b"null" in lib.s2l_last_error()
+    assert lib.s2l_rgb_forward_auto(p16, p16, -1, None, p16, 2, 3, 1, p16, None) == 2
+    assert lib.s2l_rgb_forward_auto(p16, p16, 4, None, p16, 5, 3, 1, p16, None) == 2 and b"uv_dims" in lib.s2l_last_error()
+    assert lib.s2l_audio_merge_auto(None, None, 0, 4, None, None, None) == 1
+    assert lib.s2l_audio_merge_auto_scratch_bytes() >= 260 and lib.s2l_rgb_forward_auto_scratch_bytes() >= 4100
+    gt = _cabi.S2LGeom(n_frames=2, height=8, width=12, pts_mode=_cabi.PTS_GRID, uv_dims=2, out_ch=3)
+    assert lib.s2l_train_fwd(p16, C.byref(gt), p16, p16, p16, p16, p16, None) == 2 and b"4-tap" in lib.s2l_last_error()
+    gt.pts_mode = _cabi.PTS_GRID_ENS4
+    assert lib.s2l_train_fwd(p16, C.byref(gt), None, p16, p16, p16, p16, None) == 1
+    rows = 2 * 3 * 128                                    # 8*12*4 = 384 points = 3 tiles per frame
+    assert lib.s2l_train_workspace_bytes(C.byref(gt)) > rows * (8 * 512 * 2 + 128 + 32)
+    arr = (C.c_void_p * _cabi.NUM_PARAMS)()
+    assert lib.s2l_train_bwd(p16, C.byref(gt), p16, p16, p16, p16, p16, arr, p16, None) == 3 and b"gradient buffer" in lib.s2l_last_error()
+    assert lib.s2l_audio_train_save_floats(3) == 3 * 640 and lib.s2l_audio_train_scratch_bytes(3) == 3 * 32800 * 4
+    arr12 = (C.c_void_p * 12)()
+    assert lib.s2l_audio_train_bwd(p16, p16, 0, p16, p16, arr12, p16, 2, None) == 3
+    assert lib.s2l_blob_meta(None, None, None, None, None, None) == 1
+
+
+def test_render_lip_train_and_dropin_refuse_cpu_tensors():
+    """no CPU fallback anywhere on the product path: the training render and the drop-in's fast calls raise on CPU tensors"""
+    import speech2lip_b200 as s2l
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = s2l.TalkingFace(device=torch.device("cpu"), cfg=cfg)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.render_lip_train(torch.zeros(1, 16, 29), torch.tensor([0]), 4, 4, torch.tensor([0.0]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        with torch.no_grad():
+            m.rgb_forward(torch.zeros(8, 66), time_pts=torch.tensor([1]))
+    with pytest.raises(ValueError):
+        os.environ["S2L_DROPIN_PRECISION"] = "bf16x1"
+        try:
+            s2l.TalkingFace(device=torch.device("cpu"), cfg=cfg)
+        finally:
+            del os.environ["S2L_DROPIN_PRECISION"]
