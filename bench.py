@@ -179,6 +179,59 @@ def eager_gpu_reference(a, dev):
     return out
 
 
+def post_fusion_extras(dev, B=64, h=500, w=500, lh=80, lw=120, x0=190, y0=300):
+    """the pre-UNet part of post_fusion2_onlylip_light (tf_nerf.py:334-386) as one gather-blend kernel at the
+    reference's operating point (500x500 canonical face, 80x120 lip crop), against the REFERENCE'S OWN method on the same GPU
+    (UNet replaced by identity in both arms so that only the compose + warp part is timed).  HBM roofline: unique bytes / time."""
+    import speech2lip_b200 as s2l
+    out = {}
+    try:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        lip = torch.rand(B, lh, lw, 3, generator=g).to(dev)
+        face = torch.rand(B, h, w, 3, generator=g).to(dev)
+        gt = torch.rand(B, h, w, 3, generator=g).to(dev)
+        mask = torch.zeros(B, h, w, 3, device=dev)
+        mask[:, y0 + 5:y0 + lh - 5, x0 + 5:x0 + lw - 5] = 1
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+        coord = (torch.stack([xs, ys], -1)[None].repeat(B, 1, 1, 1) * 1.02 + 0.01).to(dev)
+
+        def timeit(fn, n=10):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); e1.synchronize()
+            return e0.elapsed_time(e1) / n
+        ms = timeit(lambda: s2l.post_fusion_compose(lip, face, gt, mask, coord, x0, y0, True, lw // 5, want_canonical=False))
+        alg = B * (h * w * (8 + 12 + 12) + h * w * 12 + h * w * 12 + lh * lw * 12)      # coord + gt + out, face, mask, lip: unique bytes
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        rec = {"frames_per_s": B / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": B, "algorithmic_bytes": alg,
+               "achieved_gbs": alg / ms / 1e6, "hbm_peak_gbs": peak, "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        try:
+            from oracle import ref_runner as RR
+            if RR.available():
+                rm = RR.model(2, 3, dev)
+                rm.post_fusion_unet = torch.nn.Identity()
+                with torch.no_grad():
+                    ref = lambda: rm.post_fusion2_onlylip(lip, face, gt, mask, x0, y0, coord, use_canonical_space=True)
+                    fused = s2l.post_fusion_compose(lip, face, gt, mask, coord, x0, y0, True, lw // 5, want_canonical=False)[0]
+                    rec["max_abs_vs_reference"] = float((fused.permute(0, 2, 3, 1) - ref()[1]).abs().max().item())
+                    rec["reference_eager_ms"] = timeit(ref, 5)
+                rec["speedup_vs_reference_eager"] = rec["reference_eager_ms"] / ms
+        except Exception as e:
+            rec["reference_eager_error"] = str(e)[:200]
+        out["post_fusion_%dx%d" % (h, w)] = rec
+    except Exception as e:
+        out["post_fusion_%dx%d" % (h, w)] = {"error": str(e)[:300], "frames_per_s": 0.0, "ms_per_step": 0.0}
+    return out
+
+
 def train_step_extras(dev, sizes=((80, 120), (256, 256)), frames=4, window=5, reps=3):
     """BASELINE.json configs[4]: a 4-frame training batch, each frame with its 5-frame sync-expert window
     (training.py:404-559: predict_lip_image for the frame, training.py:500-525: five more for the window), forward +
@@ -572,6 +625,7 @@ def run_gpu_arm(a):
         except Exception as e:
             extras["reference_gpu_eager"] = {"error": str(e)[:200], "frames_per_s": 0.0, "ms_per_step": 0.0}
         extras.update(train_step_extras(dev))
+        extras.update(post_fusion_extras(dev))
 
     t = torch.tensor([dev_ms, e2e_ms, ker_ms], device=dev, dtype=torch.float64)
     if world > 1:

@@ -34,47 +34,53 @@ __device__ __forceinline__ float merged_canon(const PfArgs& a, int b, int cy, in
   return __fadd_rn(__fmul_rn(m, lipv), __fmul_rn(__fsub_rn(1.f, m), a.face[idx]));
 }
 
-__global__ void __launch_bounds__(256) post_fusion_kernel(PfArgs a) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long npix = (long long)a.Hf * a.Wf;
-  if (gid >= npix * a.B) return;
-  const int b = (int)(gid / npix);
-  const long long pix = gid % npix;
-  const float2 g = reinterpret_cast<const float2*>(a.coord)[gid];
+// grid = (pixel blocks, batch): no 64-bit division per thread; 32-bit offsets inside a frame (an image plane is < 2^31 bytes);
+// the four taps share one base offset.  ncu on the first version: sm__throughput 73 %, DRAM 30 % — the kernel was
+// instruction-bound (611 warp-instructions per 32 pixels, mostly index arithmetic), not memory-bound.
+__device__ __forceinline__ void pf_pixel_direct(const PfArgs& a, int b, int pix) {
+  const int npix = a.Hf * a.Wf;
+  const size_t canon = (size_t)b * a.h * a.w * 3;
+  const float* __restrict__ face = a.face + canon;
+  const float* __restrict__ mask = a.mask + canon;
+  const float* __restrict__ lip = a.lip + (size_t)b * a.lh * a.lw * 3;
+  const float2 g = reinterpret_cast<const float2*>(a.coord)[(size_t)b * npix + pix];
+  const float* __restrict__ gtp = a.gt + ((size_t)b * npix + pix) * 3;
+  const float gt0 = __ldg(gtp), gt1 = __ldg(gtp + 1), gt2 = __ldg(gtp + 2);
   // grid_sampler_unnormalize, align_corners=False: ((coord + 1) * size - 1) / 2
   const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.x, 1.f), (float)a.w), 1.f), 0.5f);
   const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.y, 1.f), (float)a.h), 1.f), 0.5f);
   const float fx = floorf(ix), fy = floorf(iy);
-  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const int x0 = (int)fx, y0 = (int)fy;
   const float wx1 = __fsub_rn(ix, fx), wy1 = __fsub_rn(iy, fy);
-  const float wx0 = __fsub_rn((float)x1, ix), wy0 = __fsub_rn((float)y1, iy);
-  const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
-  const bool inx0 = x0 >= 0 && x0 < a.w, inx1 = x1 >= 0 && x1 < a.w, iny0 = y0 >= 0 && y0 < a.h, iny1 = y1 >= 0 && y1 < a.h;
-  // ---- issue every load of the pixel up front (4 taps x {mask, face, lip} x 3 channels + gt): the kernel is
-  //      latency-bound otherwise (coord -> address -> gather is a dependent chain)
-  const int tx[4] = {x0, x1, x0, x1}, ty[4] = {y0, y0, y1, y1};
+  const float wx0 = __fsub_rn((float)(x0 + 1), ix), wy0 = __fsub_rn((float)(y0 + 1), iy);
+  // accumulation order nw, ne, sw, se as in ATen's grid_sampler_2d
+  const float tw[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1), __fmul_rn(wx1, wy1)};
+  const bool inx0 = (unsigned)x0 < (unsigned)a.w, inx1 = (unsigned)(x0 + 1) < (unsigned)a.w;
+  const bool iny0 = (unsigned)y0 < (unsigned)a.h, iny1 = (unsigned)(y0 + 1) < (unsigned)a.h;
   const bool tin[4] = {iny0 && inx0, iny0 && inx1, iny1 && inx0, iny1 && inx1};
-  const float tw[4] = {wnw, wne, wsw, wse};          // accumulation order nw, ne, sw, se as in ATen's grid_sampler_2d
+  const int base = (y0 * a.w + x0) * 3;
+  const int toff[4] = {base, base + 3, base + a.w * 3, base + a.w * 3 + 3};
+  const int lbase = ((y0 - a.py0) * a.lw + (x0 - a.px0)) * 3;
+  const int loff[4] = {lbase, lbase + 3, lbase + a.lw * 3, lbase + a.lw * 3 + 3};
+  const bool lx0 = (unsigned)(x0 - a.px0) < (unsigned)a.lw, lx1 = (unsigned)(x0 + 1 - a.px0) < (unsigned)a.lw;
+  const bool ly0 = (unsigned)(y0 - a.py0) < (unsigned)a.lh, ly1 = (unsigned)(y0 + 1 - a.py0) < (unsigned)a.lh;
+  const bool lin[4] = {ly0 && lx0, ly0 && lx1, ly1 && lx0, ly1 && lx1};
+  // expanded rectangle mask (tf_nerf.py:354-363) evaluated analytically per tap
+  const bool rx0 = x0 >= a.rx0 && x0 < a.rx1, rx1 = x0 + 1 >= a.rx0 && x0 + 1 < a.rx1;
+  const bool ry0 = y0 >= a.ry0 && y0 < a.ry1, ry1 = y0 + 1 >= a.ry0 && y0 + 1 < a.ry1;
+  const bool rin[4] = {ry0 && rx0, ry0 && rx1, ry1 && rx0, ry1 && rx1};
+  // every load of the pixel is issued before the first use (coord -> address -> gather is a dependent chain)
   float mk[4][3], fc[4][3], lp[4][3];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { mk[t][c] = 0.f; fc[t][c] = 0.f; lp[t][c] = 0.f; }
-    if (tin[t]) {
-      const size_t idx = (((size_t)b * a.h + ty[t]) * a.w + tx[t]) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { mk[t][c] = __ldg(a.mask + idx + c); fc[t][c] = __ldg(a.face + idx + c); }
-      const int ly = ty[t] - a.py0, lx = tx[t] - a.px0;
-      if (ly >= 0 && ly < a.lh && lx >= 0 && lx < a.lw) {
-        const size_t li = (((size_t)b * a.lh + ly) * a.lw + lx) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) lp[t][c] = __ldg(a.lip + li + c);
-      }
+    for (int c = 0; c < 3; ++c) {
+      mk[t][c] = tin[t] ? __ldg(mask + toff[t] + c) : 0.f;
+      fc[t][c] = tin[t] ? __ldg(face + toff[t] + c) : 0.f;
+      lp[t][c] = (tin[t] && lin[t]) ? __ldg(lip + loff[t] + c) : 0.f;
     }
   }
-  float gtv[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) gtv[c] = __ldg(a.gt + gid * 3 + c);
+  const float gtv[3] = {gt0, gt1, gt2};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float acc = 0.f, macc = 0.f;
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) post_fusion_kernel(PfArgs a) {
         // merged_canonical = m*lip_pad + (1-m)*face   (tf_nerf.py:352), then the bilinear tap
         const float mc = __fadd_rn(__fmul_rn(mk[t][c], lp[t][c]), __fmul_rn(__fsub_rn(1.f, mk[t][c]), fc[t][c]));
         acc = __fadd_rn(acc, __fmul_rn(mc, tw[t]));
-        const float mv = a.rect ? ((ty[t] >= a.ry0 && ty[t] < a.ry1 && tx[t] >= a.rx0 && tx[t] < a.rx1) ? 1.f : 0.f) : mk[t][c];
+        const float mv = a.rect ? (rin[t] ? 1.f : 0.f) : mk[t][c];
         macc = __fadd_rn(macc, __fmul_rn(mv, tw[t]));
       }
     }
@@ -92,6 +98,15 @@ __global__ void __launch_bounds__(256) post_fusion_kernel(PfArgs a) {
     a.fused[((size_t)b * 3 + c) * npix + pix] = (macc != 0.f) ? acc : gtv[c];
   }
 }
+
+__global__ void __launch_bounds__(256) post_fusion_kernel(PfArgs a) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < a.Hf * a.Wf) pf_pixel_direct(a, blockIdx.y, pix);
+}
+
+// (A tiled variant — the block stages merged_canonical of its tile's canonical bounding box in shared memory and the pixels
+// gather from there — was built and measured: 0.41 ms vs 0.31 ms for this direct kernel on 64 frames of 500x500; the bounding-box
+// reduction, the fill phase and its barriers cost more than the 4x texel reuse saves while the taps already hit L1.  Removed.)
 
 __global__ void merged_canonical_kernel(PfArgs a, float* __restrict__ out) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,8 +154,11 @@ extern "C" int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* fa
   }
   if (batch == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long n = (long long)batch * out_h * out_w;
-  post_fusion_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+  if ((long long)face_h * face_w * 3 >= 0x7fffffffll || (long long)out_h * out_w >= 0x7fffffffll || batch > 65535) {
+    set_error("s2l_post_fusion_compose: image planes beyond 2^31 elements / batch beyond 65535 are not supported");
+    return 2;
+  }
+  post_fusion_kernel<<<dim3((unsigned)((out_h * out_w + 255) / 256), (unsigned)batch), 256, 0, st>>>(a);
   if (!check_launch("post_fusion_kernel")) return 5;
   if (merged_canonical) {
     const long long m = (long long)batch * face_h * face_w * 3;

@@ -159,7 +159,7 @@ def test_synth_generators_are_shared_not_duplicated():
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         for node in ast.walk(fn):
             if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
-                assert fn.name in ("reference_runner", "oracle_port_runner", "eager_gpu_reference", "train_step_extras"), "bench.py imports oracle/ in %s()" % fn.name
+                assert fn.name in ("reference_runner", "oracle_port_runner", "eager_gpu_reference", "train_step_extras", "post_fusion_extras"), "bench.py imports oracle/ in %s()" % fn.name
     for node in tree.body:
         assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node)), "module-level oracle import"
 
