@@ -108,11 +108,17 @@ class FusedMLPRows(torch.autograd.Function):
             for n in ("fc_time", "fc_time_skip"):
                 g[n + ".weight"] = torch.zeros_like(P[n + ".weight"])
                 g[n + ".bias"] = torch.zeros_like(P[n + ".bias"])
-        # ---- input gradient: latent columns only (coordinates are constants in the reference's training loop)
+        # ---- input gradient: the latent columns and — a caller may differentiate w.r.t. the coordinates too (learnable warps,
+        #      depth) — the uv columns through the positional encoding's Jacobian (1, f cos(f x), -f sin(f x)), tf_nerf.py:404-425
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.zeros_like(x)
+            dx = torch.empty_like(x)
             dx[:, D:] = d_net @ P["fc_audio.weight"] + d_skip @ P["fc_audio_skip.weight"]
+            d_pe = d_net @ P["fc_uv.weight"] + d_skip @ P["fc_uv_skip.weight"]              # [N, D + 20 D]
+            freqs = (2.0 ** torch.arange(10, device=x.device, dtype=torch.float32))          # 2**linspace(0, 9, 10)
+            ang = x[:, None, :D] * freqs[None, :, None]                                       # [N, 10, D]
+            blocks = d_pe[:, D:].reshape(N, 10, 2, D)                                         # per frequency: (sin block, cos block)
+            dx[:, :D] = d_pe[:, :D] + ((blocks[:, :, 0] * torch.cos(ang) - blocks[:, :, 1] * torch.sin(ang)) * freqs[None, :, None]).sum(1)
         grads = [g[n] if ctx.needs_input_grad[4 + i] else None for i, n in enumerate(param_order())]
         return (dx, None, None, None, *grads)
 

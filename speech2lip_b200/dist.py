@@ -17,8 +17,9 @@ def shard_frames(n_frames, rank, world_size):
 
 
 def broadcast_params(params, src=0, group=None):
-    """In-place broadcast of the hot-path tensors (reference state_dict names) from `src` as ONE flat
-    fp32 buffer (<= 2.8 MB).  Works on NCCL (cuda tensors) and gloo (cpu tensors)."""
+    """In-place broadcast of the 42 HOT-PATH tensors (reference state_dict names) from `src` as ONE flat fp32 buffer
+    (<= 2.8 MB): all an inference renderer needs.  It is NOT a replacement for DDP's constructor broadcast of a training
+    module — use broadcast_module for that.  Works on NCCL (cuda tensors) and gloo (cpu tensors)."""
     names = [n for n in PARAM_NAMES]
     tensors = [params[n] for n in names]
     flat = torch.cat([t.detach().reshape(-1).float() for t in tensors])
@@ -30,6 +31,25 @@ def broadcast_params(params, src=0, group=None):
             t.copy_(flat[off:off + n].view_as(t))
             off += n
     return params
+
+
+def broadcast_module(module, src=0, group=None):
+    """What DistributedDataParallel's constructor does for the WHOLE module (training.py:40): every parameter AND buffer
+    (the post-fusion UNet, its BatchNorm running statistics, canonical_depth_head, coord_linears included) from `src`,
+    one flat broadcast per dtype.  broadcast_params above covers only the 42 hot-path tensors a renderer needs."""
+    by_dtype = {}
+    for t in list(module.parameters()) + list(module.buffers()):
+        by_dtype.setdefault(t.dtype, []).append(t)
+    with torch.no_grad():
+        for dtype, ts in by_dtype.items():
+            flat = torch.cat([t.detach().reshape(-1) for t in ts])
+            dist.broadcast(flat, src=src, group=group)
+            off = 0
+            for t in ts:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))
+                off += n
+    return module
 
 
 def gather_frames(local_rgb, n_frames, group=None):

@@ -25,7 +25,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import synth
-    from speech2lip_b200.dist import broadcast_params, gather_frames, shard_frames
+    from speech2lip_b200.dist import broadcast_params, broadcast_module, gather_frames, shard_frames
     # rank 0 holds the real weights, rank 1 garbage: after ONE broadcast both must agree
     sd = {k: torch.from_numpy(v).clone() for k, v in synth.make_state_dict(seed=rank, kind="default").items()}
     broadcast_params(sd, src=0)
@@ -35,7 +35,21 @@ def _worker(rank, world, port, q):
     local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1, 1).expand(-1, 2, 2, 3).contiguous()
     full = gather_frames(local, 5)
     ok_gather = torch.equal(full[:, 0, 0, 0], torch.arange(5, dtype=torch.float32))
-    q.put((rank, same, ok_gather, (lo, hi)))
+    # the whole training module (UNet weights, BatchNorm running statistics / int64 counters, depth head): DDP's constructor broadcast
+    import json
+    import speech2lip_b200 as s2l
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    torch.manual_seed(100 + rank)
+    m = s2l.TalkingFace(device=torch.device("cpu"), cfg=cfg)
+    m.post_fusion_unet.inc.double_conv[1].running_mean.fill_(float(rank) + 0.5)
+    m.post_fusion_unet.inc.double_conv[1].num_batches_tracked.fill_(7 + rank)
+    broadcast_module(m, src=0)
+    digest = torch.stack([t.double().sum() for t in list(m.parameters()) + list(m.buffers())]).sum().reshape(1)
+    both = [torch.empty_like(digest) for _ in range(world)]
+    dist.all_gather(both, digest)
+    same_module = bool(torch.equal(both[0], both[1])) and float(m.post_fusion_unet.inc.double_conv[1].running_mean[0]) == 0.5 \
+        and int(m.post_fusion_unet.inc.double_conv[1].num_batches_tracked) == 7
+    q.put((rank, same and same_module, ok_gather, (lo, hi)))
     dist.destroy_process_group()
 
 

@@ -482,6 +482,27 @@ def test_training_backward_vs_oracle_autograd(S, kind):
     assert m.coord_linears[0].weight.grad is None
 
 
+def test_training_backward_reaches_the_coordinates(S):
+    """a caller may differentiate w.r.t. the uv columns too (learnable warps): the per-call backward returns the gradient
+    through the positional encoding's Jacobian, not silent zeros (advisor finding, round 1)."""
+    import json
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    sd_np = synth.make_state_dict(0, "kaiming")
+    m = S.TalkingFace(device=dev(), cfg=cfg).to(dev()).train()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()}, strict=False)
+    g = torch.Generator().manual_seed(3)
+    x = torch.cat([torch.rand(300, 2, generator=g), torch.randn(300, 64, generator=g) * 0.1], -1)
+    gout = torch.randn(300, 3, generator=g)
+    xo = x.clone().requires_grad_(True)
+    (O.rgb_forward(O.to_torch_sd(sd_np), xo, torch.tensor([4])) * gout).sum().backward()
+    xg = x.to(dev()).requires_grad_(True)
+    (m.rgb_forward(xg, time_pts=torch.tensor([4])) * gout.to(dev())).sum().backward()
+    e_uv = ((xg.grad[:, :2].cpu() - xo.grad[:, :2]).norm() / xo.grad[:, :2].norm()).item()
+    e_lat = ((xg.grad[:, 2:].cpu() - xo.grad[:, 2:]).norm() / xo.grad[:, 2:].norm()).item()
+    print("d/d(uv) vs oracle autograd: %.2e, d/d(latent): %.2e" % (e_uv, e_lat))
+    assert e_uv < 1e-4 and e_lat < 1e-4 and xo.grad[:, :2].abs().max() > 0
+
+
 def test_training_step_changes_output_and_repacks(S):
     """an optimizer step updates the parameters in place -> the packed blob must follow (tensor._version tracking)."""
     cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
