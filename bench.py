@@ -776,6 +776,8 @@ def run_config3(a):
     # ---- optional gather of the finished frames (uint8 BGR, what the reference writes) onto every rank: one all_gather
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     u8 = R.frames_to_bgr8(out[:hi - lo])
+    if world > 1:
+        gather_frames(u8[:1], world)                          # warm-up: NCCL sets up the all_gather channels on first use
     barrier()
     g0.record()
     allf = gather_frames(u8, T) if world > 1 else u8

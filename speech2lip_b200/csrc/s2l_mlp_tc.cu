@@ -422,9 +422,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             else tmem_st16(taddr, o);
 #ifndef S2L_DBG_NOSAVEH
             if (TRAIN && tile < n_tiles) {     // h_g as the next layer consumes it: 32 bf16 = 64 B of this row
-              uint4* dst = reinterpret_cast<uint4*>(a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+              __nv_bfloat16* dst = a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32;
+              st_global_v8(dst, o);
+              st_global_v8(dst + 16, o + 8);
             }
 #endif
             tmem_st_wait();

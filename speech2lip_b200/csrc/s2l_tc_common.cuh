@@ -166,6 +166,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.256).  The training kernels move 64-byte row segments per thread at a 512-byte
+// row stride: with 128-bit accesses every warp instruction is 32 HALF-filled 32-byte sectors, with 256-bit ones 32 full sectors
+// in half as many instructions.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+               "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
 // ------------------------------------------------------------------ thread-block-cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -46,8 +46,7 @@ struct DgArgs {
 
 // fp32 accumulator slice (32 columns) + the matching 32 saved activations (16 packed bf16 pairs) -> 16 packed bf16 pairs of
 // dPre = dH * [h > 0]
-__device__ __forceinline__ void mask_slice(const uint32_t (&v)[32], const uint4 (&hm)[4], uint32_t (&o)[16]) {
-  const uint32_t* hw = reinterpret_cast<const uint32_t*>(hm);
+__device__ __forceinline__ void mask_slice(const uint32_t (&v)[32], const uint32_t (&hw)[16], uint32_t (&o)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float x0 = (hw[j] & 0x00007FFFu) ? __uint_as_float(v[2 * j]) : 0.f;
@@ -215,9 +214,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
       // the bias gradient sums the same bf16 values the weight-gradient GEMM multiplies
       sb0 += __uint_as_float(lo.x << 16); sb1 += __uint_as_float(lo.x & 0xffff0000u); sb2 += __uint_as_float(lo.y << 16);
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-      uint4* g16 = reinterpret_cast<uint4*>(a.B.dout16 + ((size_t)tile * TC_TM + r) * 16);
-      g16[0] = lo;
-      g16[1] = zero;
+      {
+        const uint32_t w8[8] = {lo.x, lo.y, 0u, 0u, 0u, 0u, 0u, 0u};
+        st_global_v8(a.B.dout16 + ((size_t)tile * TC_TM + r) * 16, w8);
+      }
       mbar_wait_wd<true>(&do_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), 500 + buf);
       uint8_t* img = smem + DG_SM_DOUT + buf * PE_PLANE + (r >> 3) * 1024 + (r & 7) * 128;
       *reinterpret_cast<uint4*>(img + ((0 ^ (r & 7)) << 4)) = lo;
@@ -253,12 +253,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
         __nv_bfloat16* drow = a.B.dpre + ((size_t)hl * RT + grow) * 256;
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
-          uint4 hm[2][4];
+          uint32_t hm[2][16];
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {
-            const uint4* src = reinterpret_cast<const uint4*>(hrow + hh * 128 + qq * 64 + half * 32);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) hm[qq][t] = __ldg(src + t);
+            const __nv_bfloat16* src = hrow + hh * 128 + qq * 64 + half * 32;
+            ld_global_nc_v8(src, hm[qq]);
+            ld_global_nc_v8(src + 16, hm[qq] + 8);
           }
           if (step == 0) {
             mbar_wait_wd(&acc_t8[hh], (uint32_t)(it & 1), 710 + hh);
@@ -277,9 +277,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
             tmem_ld_wait();
             mask_slice(v, hm[qq], o);
             if (step < 7) tmem_st16(taddr, o);          // dPre0 feeds no further layer
-            uint4* dst = reinterpret_cast<uint4*>(drow + q * 64 + half * 32);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) dst[t] = make_uint4(o[4 * t], o[4 * t + 1], o[4 * t + 2], o[4 * t + 3]);
+            st_global_v8(drow + q * 64 + half * 32, o);
+            st_global_v8(drow + q * 64 + half * 32 + 16, o + 8);
             if (step < 7) {
               tmem_st_wait();
               tc_fence_before();
