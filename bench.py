@@ -306,6 +306,24 @@ def train_step_extras(dev, sizes=((80, 120), (256, 256)), frames=4, window=5, re
                             ropt.step()
                     rec["reference_eager_ms"] = timeit(ref_step, 2)
                     rec["speedup_vs_reference_eager"] = rec["reference_eager_ms"] / best
+                    # the UNMODIFIED caller: the reference's own Trainer.predict_lip_image driving the drop-in, call by call
+                    # (4 rgb_forward calls per render), exact fp32 kernels and the opt-in bf16 tensor-core per-call path
+                    mtr = RR.trainer(m, dev, H, W)
+
+                    def dropin_step():
+                        for f in range(frames):
+                            opt.zero_grad(set_to_none=True)
+                            loss = 0
+                            for j in range(G):
+                                i = f * G + j
+                                rgb = mtr.predict_lip_image(0, coords, audio[i:i + 1], None, {"index": index[i:i + 1].to(dev)}, None, None, None)
+                                loss = loss + ((rgb.view(H, W, 3) - target[i]) ** 2).mean() / G
+                            loss.backward()
+                            opt.step()
+                    for tp in ("fp32", "bf16"):
+                        m.train_precision = tp
+                        rec["unmodified_trainer_ms_%s" % tp] = timeit(dropin_step, 2)
+                    m.train_precision = "fp32"
                     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
                     del rm, tr, ropt
             except Exception as e:

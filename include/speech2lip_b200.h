@@ -222,6 +222,17 @@ int32_t s2l_train_fwd(const void* blob, const S2LGeom* geom, const float* latent
 int32_t s2l_train_bwd(const void* blob, const S2LGeom* geom, const float* d_rgb, const float* latent, const int64_t* frame_idx,
                       const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream);
 
+/* The same kernels behind the reference's PER-CALL contract: autograd through ONE rgb_forward call (tf_nerf.py:225-285) whose
+ * N rows share one latent — what Trainer.predict_lip_image passes four times per frame (training.py:216-233).  x [N,66] (the
+ * coordinates are read in place, the latent from row 0), time_idx_dev = DEVICE int64[1] or NULL, out [N,3] raw outputs;
+ * the backward writes the 30 MLP gradients like s2l_train_bwd and d_latent [64] (the gradient of the shared latent = the sum
+ * over the rows).  bf16; the exact fp32 path of the contract is s2l_rgb_forward_rows_train / s2l_mlp_bwd_rows. */
+size_t  s2l_train_rows_workspace_bytes(int64_t n_rows);
+int32_t s2l_train_rows_fwd(const void* blob, const float* x, int64_t n_rows, const int64_t* time_idx_dev, float* out,
+                           float* frame_bias, void* workspace, void* stream);
+int32_t s2l_train_rows_bwd(const void* blob, const float* d_out, const float* x, int64_t n_rows, const int64_t* time_idx_dev,
+                           const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream);
+
 /* Replaces: Embedder.__call__ (tf_nerf.py:404-425): x rows (first uv_dims floats of each row_stride-float row) -> pe [N,E]. */
 int32_t s2l_embed_fwd(const float* x, int64_t n_rows, int32_t row_stride, int32_t uv_dims, float* pe, void* stream);
 

@@ -245,3 +245,52 @@ class AudioNetFn(torch.autograd.Function):
 def audio_merge_forward_train(module, audio):
     sd = module._hot_params()
     return AudioNetFn.apply(audio, module.packed_weights(), *[sd[n] for n in AUDIO_PARAM_NAMES])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The per-call contract on the tensor-core training kernels (opt-in, bf16): one rgb_forward call whose rows share one latent
+# (what the unmodified Trainer.predict_lip_image passes, training.py:216-233).  s2l_train_rows_fwd / s2l_train_rows_bwd.
+class FusedMLPRowsTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, time_idx, packed, *params):
+        lib = _cabi.lib()
+        x = x.contiguous().float()
+        N = x.shape[0]
+        dev = x.device
+        tdev = None if time_idx is None else torch.as_tensor(time_idx).reshape(-1)[:1].to(device=dev, dtype=torch.int64)
+        out = torch.empty(N, 3, device=dev)
+        bias = torch.empty(1, 4, 256, device=dev)
+        ws = torch.empty(lib.s2l_train_rows_workspace_bytes(N), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(lib.s2l_train_rows_fwd(_ptr(packed.blob), _ptr(x), N, _ptr(tdev), _ptr(out), _ptr(bias), _ptr(ws), _stream()),
+                        "s2l_train_rows_fwd")
+        ctx.packed = packed
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.has_time = tdev is not None
+        ctx.save_for_backward(x, bias, ws, tdev if tdev is not None else torch.empty(0, device=dev))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _cabi.lib()
+        x, bias, ws, tdev = ctx.saved_tensors
+        dev = x.device
+        d_out = d_out.contiguous().float()
+        grads = [torch.empty(sh, device=dev) for sh in ctx.shapes]
+        d_latent = torch.empty(64, device=dev)
+        arr = (C.c_void_p * _cabi.NUM_PARAMS)(*([None] * 12 + [g.data_ptr() for g in grads]))
+        with torch.cuda.device(dev):
+            _cabi.check(lib.s2l_train_rows_bwd(_ptr(ctx.packed.blob), _ptr(d_out), _ptr(x), x.shape[0], _ptr(tdev if ctx.has_time else None),
+                                               _ptr(bias), _ptr(ws), arr, _ptr(d_latent), _stream()), "s2l_train_rows_bwd")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # every row carries the same latent: its gradient is the sum over the rows, returned on row 0 (whatever tiled the
+            # latent — tile / expand — sums the rows' gradients anyway); no coordinate gradient on this path
+            dx = torch.zeros_like(x)
+            dx[0, 2:] = d_latent
+        return (dx, None, None, *grads)
+
+
+def rgb_forward_train_tc(module, x, time_pts):
+    sd = module._hot_params()
+    return FusedMLPRowsTC.apply(x, time_pts, module.packed_weights(), *[sd[n] for n in MLP_PARAM_NAMES])

@@ -607,7 +607,7 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
 // Training forward (s2l_train_fwd): the live 4-tap render of F frames in bf16 with the fused blend epilogue, saving the
 // activations the backward needs.  Always the single-CTA schedule (training launches are a few thousand tiles).
 int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* rgb,
-                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st) {
+                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st, float* raw_out) {
   TcArgs a{};
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
@@ -616,14 +616,18 @@ int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, con
   a.out_ch = 3;
   a.n_frames = n_frames;
   a.tiles_per_frame = (src.P + TC_TM - 1) / TC_TM;
-  a.epi_mode = EPI_ENS4;
+  a.epi_mode = raw_out ? EPI_RAW : EPI_ENS4;      // raw_out: the per-call rows contract (explicit points, raw [N,3] outputs)
   a.rgb = rgb;
+  a.out = raw_out;
   a.save_h = save_h;
   a.save_pe = save_pe;
   const long long n_tiles = a.tiles_per_frame * n_frames;
   a.rows_total = n_tiles * TC_TM;
   if (n_tiles == 0) return 0;
-  if (src.mode != S2L_PTS_GRID_ENS4 || src.uv_dims != 2) { set_error("mlp_tc_train: the training render is the 4-tap live mode (uv_dims = 2)"); return 2; }
+  if (src.uv_dims != 2 || (raw_out ? src.mode != S2L_PTS_EXPLICIT : src.mode != S2L_PTS_GRID_ENS4)) {
+    set_error("mlp_tc_train: 4-tap live render (GRID_ENS4) or explicit rows, uv_dims = 2");
+    return 2;
+  }
   return launch_tc_impl<1, 2, 1, true>(a, n_tiles, st);
 }
 

@@ -40,7 +40,8 @@ struct DgArgs {
   PointSrc src;               // GRID_ENS4
   int n_frames;
   long long tiles_per_frame;
-  const float* d_rgb;         // [F, H*W, 3]
+  const float* d_rgb;         // [F, H*W, 3]   (4-tap render) ...
+  const float* d_out_rows;    // ... or [N,3] gradient of the raw outputs (per-call rows contract, explicit points)
   TrainBufs B;
 };
 
@@ -200,7 +201,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
       const int f = (int)(tile / a.tiles_per_frame);
       const long long p = (tile % a.tiles_per_frame) * TC_TM + r;
       float d[3] = {0.f, 0.f, 0.f};
-      if (p < a.src.P) {
+      if (a.d_out_rows) {
+        if (p < a.src.P) {
+          const float* g = a.d_out_rows + ((long long)f * a.src.P + p) * 3;
+          d[0] = g[0]; d[1] = g[1]; d[2] = g[2];
+        }
+      } else if (p < a.src.P) {
         // weight of this tap in the blend: area of the OPPOSITE tap / total area (training.py:237-249)
         const long long pix = p >> 2;
         const int tap = (int)(p & 3);
@@ -299,8 +305,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
   }
 }
 
-int launch_dgrad_tc(const void* blob, const PointSrc& src, int n_frames, const float* d_rgb, const TrainBufs& B, cudaStream_t st) {
+int launch_dgrad_tc(const void* blob, const PointSrc& src, int n_frames, const float* d_rgb, const TrainBufs& B, cudaStream_t st,
+                    const float* d_out_rows) {
   DgArgs a{};
+  a.d_out_rows = d_out_rows;
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
   a.src = src;

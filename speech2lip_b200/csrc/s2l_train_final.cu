@@ -8,8 +8,9 @@
 namespace s2l {
 
 int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* rgb,
-                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st);
-int launch_dgrad_tc(const void* blob, const PointSrc& src, int n_frames, const float* d_rgb, const TrainBufs& B, cudaStream_t st);
+                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st, float* raw_out = nullptr);
+int launch_dgrad_tc(const void* blob, const PointSrc& src, int n_frames, const float* d_rgb, const TrainBufs& B, cudaStream_t st,
+                    const float* d_out_rows = nullptr);
 int launch_wgrad_tc(const WgPlan& plan, const TrainBufs& B, cudaStream_t st);
 
 struct GradPtrs {
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) wg_frame_terms_kernel(const uint8_t* __re
   if (r < nT) {
     const int which = (int)(r / (256 * 20)), j = (int)((r / 20) % 256), k = (int)(r % 20);
     float s = 0.f;
-    for (int f = 0; f < F; ++f) {
+    for (int f = 0; f < F && frame_idx; ++f) {                                      // no time input: the term is absent, gradient 0
       const float ang = __fmul_rn((float)frame_idx[f], C[C_DIV + (k >> 1)]);      // tf_nerf.py:439-440
       s = fmaf(gvec(which, f)[j], (k & 1) ? cosf(ang) : sinf(ang), s);
     }
@@ -165,10 +166,11 @@ __global__ void __launch_bounds__(256) wg_frame_terms_kernel(const uint8_t* __re
     const int which = (int)(r >> 8), j = (int)(r & 255);
     float s = 0.f;
     for (int f = 0; f < F; ++f) s += gvec(which, f)[j];
+    const float st = frame_idx ? s : 0.f;
     if (which) {
-      G.g[S2L_P_FC_UV_SKIP_B][j] = s; G.g[S2L_P_FC_AUDIO_SKIP_B][j] = s; G.g[S2L_P_FC_TIME_SKIP_B][j] = s;
+      G.g[S2L_P_FC_UV_SKIP_B][j] = s; G.g[S2L_P_FC_AUDIO_SKIP_B][j] = s; G.g[S2L_P_FC_TIME_SKIP_B][j] = st;
     } else {
-      G.g[S2L_P_FC_UV_B][j] = s; G.g[S2L_P_FC_AUDIO_B][j] = s; G.g[S2L_P_FC_TIME_B][j] = s;
+      G.g[S2L_P_FC_UV_B][j] = s; G.g[S2L_P_FC_AUDIO_B][j] = s; G.g[S2L_P_FC_TIME_B][j] = st;
     }
     return;
   }
@@ -188,12 +190,11 @@ struct TrainLayout {
   long long rows_total;
   size_t off_h, off_pe, off_dpre, off_dout, off_part, off_red, off_dbout, total;
 };
-static TrainLayout train_layout(const S2LGeom& g, int sms) {
+static TrainLayout train_layout_pts(long long P, int n_frames, int sms) {
   TrainLayout t{};
-  const long long P = (long long)g.height * g.width * 4;
   const long long tiles = (P + 127) / 128;
-  t.rows_total = tiles * 128 * (g.n_frames > 0 ? g.n_frames : 0);
-  const WgPlan pl = make_wg_plan(g.n_frames, tiles, sms);
+  t.rows_total = tiles * 128 * (n_frames > 0 ? n_frames : 0);
+  const WgPlan pl = make_wg_plan(n_frames, tiles, sms);
   auto al = [](size_t x) { return (x + 1023) & ~size_t(1023); };
   size_t o = 0;
   t.off_h = o;    o = al(o + (size_t)8 * t.rows_total * 256 * 2);
@@ -201,10 +202,13 @@ static TrainLayout train_layout(const S2LGeom& g, int sms) {
   t.off_dpre = o; o = al(o + (size_t)8 * t.rows_total * 256 * 2);
   t.off_dout = o; o = al(o + (size_t)t.rows_total * 16 * 2);
   t.off_part = o; o = al(o + (size_t)pl.total_floats() * 4);
-  t.off_red = o;  o = al(o + (size_t)red_floats(g.n_frames) * 4);
+  t.off_red = o;  o = al(o + (size_t)red_floats(n_frames) * 4);
   t.off_dbout = o; o = al(o + (size_t)kDboutRows * 4 * 4);
   t.total = o;
   return t;
+}
+static TrainLayout train_layout(const S2LGeom& g, int sms) {
+  return train_layout_pts((long long)g.height * g.width * 4, g.n_frames, sms);
 }
 static int sm_count() {
   int dev = 0, sms = 148;
@@ -258,20 +262,17 @@ extern "C" int32_t s2l_train_fwd(const void* blob, const S2LGeom* geom, const fl
                              reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe), reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int32_t s2l_train_bwd(const void* blob, const S2LGeom* geom, const float* d_rgb, const float* latent, const int64_t* frame_idx,
-                                 const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream) {
-  if (int e = check_train_geom(geom, "s2l_train_bwd")) return e;
-  if (geom->n_frames == 0 || geom->height * geom->width == 0) return 0;
-  if (!blob || !d_rgb || !latent || !frame_idx || !frame_bias || !workspace || !grads_host || !d_latent) { set_error("s2l_train_bwd: null argument"); return 1; }
+// dgrad -> wgrad -> slab reduction -> fold chain rule -> per-frame terms, shared by the render and the rows entry points
+static int train_backward(const void* blob, const PointSrc& src, int F, const TrainLayout& t, const float* d_rgb, const float* d_out_rows,
+                          const float* latent, const int64_t* frame_idx, const float* frame_bias, void* workspace,
+                          float* const* grads_host, float* d_latent, cudaStream_t st, const char* who) {
   GradPtrs G{};
   for (int i = S2L_P_FC_UV_W; i < S2L_NUM_PARAMS; ++i) {
-    if (!grads_host[i]) { set_error("s2l_train_bwd: gradient buffer %d is null", i); return 3; }
+    if (!grads_host[i]) { set_error("%s: gradient buffer %d is null", who, i); return 3; }
     G.g[i] = grads_host[i];
   }
   G.d_latent = d_latent;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
-  const TrainLayout t = train_layout(*geom, sms);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   TrainBufs B{};
   B.h = reinterpret_cast<__nv_bfloat16*>(ws + t.off_h);
@@ -281,16 +282,15 @@ extern "C" int32_t s2l_train_bwd(const void* blob, const S2LGeom* geom, const fl
   B.partials = reinterpret_cast<float*>(ws + t.off_part);
   B.dbout_part = reinterpret_cast<float*>(ws + t.off_dbout);
   B.rows_total = t.rows_total;
-  if (cudaMemsetAsync(B.dbout_part, 0, (size_t)kDboutRows * 4 * 4, st) != cudaSuccess) { set_error("s2l_train_bwd: cudaMemsetAsync failed"); return 5; }
+  if (cudaMemsetAsync(B.dbout_part, 0, (size_t)kDboutRows * 4 * 4, st) != cudaSuccess) { set_error("%s: cudaMemsetAsync failed", who); return 5; }
   float* red = reinterpret_cast<float*>(ws + t.off_red);
-  const PointSrc src = train_src(*geom);
   const long long tiles = (src.P + 127) / 128;
-  const WgPlan pl = make_wg_plan(geom->n_frames, tiles, sms);
+  const WgPlan pl = make_wg_plan(F, tiles, sms);
   int rc;
-  if ((rc = launch_dgrad_tc(blob, src, geom->n_frames, d_rgb, B, st))) return rc;
+  if ((rc = launch_dgrad_tc(blob, src, F, d_rgb, B, st, d_out_rows))) return rc;
   if ((rc = launch_wgrad_tc(pl, B, st))) return rc;
   const Layout L = blob_layout();
-  const int F = geom->n_frames, E = pe_dim(2);
+  const int E = pe_dim(2);
   {
     const long long n = 7ll * 65536 + 7ll * 256 + 2ll * 16384 + 2ll * F * 256 + 256ll * 4 + 4;
     wg_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pl, B.partials, G, red, B.dbout_part, kDboutRows, 3);
@@ -308,4 +308,48 @@ extern "C" int32_t s2l_train_bwd(const void* blob, const S2LGeom* geom, const fl
     if (!check_launch("wg_frame_terms_kernel")) return 5;
   }
   return 0;
+}
+
+extern "C" int32_t s2l_train_bwd(const void* blob, const S2LGeom* geom, const float* d_rgb, const float* latent, const int64_t* frame_idx,
+                                 const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream) {
+  if (int e = check_train_geom(geom, "s2l_train_bwd")) return e;
+  if (geom->n_frames == 0 || geom->height * geom->width == 0) return 0;
+  if (!blob || !d_rgb || !latent || !frame_idx || !frame_bias || !workspace || !grads_host || !d_latent) { set_error("s2l_train_bwd: null argument"); return 1; }
+  return train_backward(blob, train_src(*geom), geom->n_frames, train_layout(*geom, sm_count()), d_rgb, nullptr, latent, frame_idx, frame_bias,
+                        workspace, grads_host, d_latent, reinterpret_cast<cudaStream_t>(stream), "s2l_train_bwd");
+}
+
+// ---- the per-call rows contract on the tensor-core training kernels (bf16): rows that share ONE latent
+static PointSrc rows_src(const float* x, long long n_rows) {
+  PointSrc s{};
+  s.mode = S2L_PTS_EXPLICIT;
+  s.uv_dims = 2;
+  s.S = s.Sc = 1;
+  s.P = n_rows;
+  s.pts = x;
+  s.pts_stride = 2 + kLatent;
+  return s;
+}
+extern "C" size_t s2l_train_rows_workspace_bytes(int64_t n_rows) {
+  return n_rows > 0 ? train_layout_pts(n_rows, 1, sm_count()).total : 0;
+}
+extern "C" int32_t s2l_train_rows_fwd(const void* blob, const float* x, int64_t n_rows, const int64_t* time_idx_dev, float* out,
+                                      float* frame_bias, void* workspace, void* stream) {
+  if (n_rows < 0) { set_error("s2l_train_rows_fwd: negative n_rows"); return 2; }
+  if (n_rows == 0) return 0;
+  if (!blob || !x || !out || !frame_bias || !workspace) { set_error("s2l_train_rows_fwd: null argument"); return 1; }
+  const TrainLayout t = train_layout_pts(n_rows, 1, sm_count());
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = s2l_latent_bias_fwd(blob, x + 2, 2 + kLatent, time_idx_dev, frame_bias, 1, stream);
+  if (rc) return rc;
+  return launch_mlp_tc_train(blob, rows_src(x, n_rows), 1, frame_bias, nullptr, reinterpret_cast<__nv_bfloat16*>(ws + t.off_h),
+                             reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe), reinterpret_cast<cudaStream_t>(stream), out);
+}
+extern "C" int32_t s2l_train_rows_bwd(const void* blob, const float* d_out, const float* x, int64_t n_rows, const int64_t* time_idx_dev,
+                                      const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream) {
+  if (n_rows < 0) { set_error("s2l_train_rows_bwd: negative n_rows"); return 2; }
+  if (n_rows == 0) return 0;
+  if (!blob || !d_out || !x || !frame_bias || !workspace || !grads_host || !d_latent) { set_error("s2l_train_rows_bwd: null argument"); return 1; }
+  return train_backward(blob, rows_src(x, n_rows), 1, train_layout_pts(n_rows, 1, sm_count()), nullptr, d_out, x + 2, time_idx_dev, frame_bias,
+                        workspace, grads_host, d_latent, reinterpret_cast<cudaStream_t>(stream), "s2l_train_rows_bwd");
 }

@@ -178,6 +178,12 @@ class TalkingFace(nn.Module):
         if self.dropin_precision not in ("bf16x3", "fp16f8", "fp32"):
             raise ValueError("S2L_DROPIN_PRECISION must be bf16x3, fp16f8 (parity modes) or fp32, got %r" % self.dropin_precision)
         self.dropin_min_rows = 1024
+        # Per-call training arithmetic (rgb_forward under autograd): "fp32" = exact kernels (default, what the reference computes),
+        # "bf16" = the tensor-core training kernels for calls whose rows share one latent (S2L_TRAIN_PRECISION).  The batched
+        # render_lip_train is always bf16.
+        self.train_precision = os.environ.get("S2L_TRAIN_PRECISION", "fp32")
+        if self.train_precision not in ("fp32", "bf16"):
+            raise ValueError("S2L_TRAIN_PRECISION must be fp32 or bf16, got %r" % self.train_precision)
 
     # ------------------------------------------------------------------ packed weights (kernel layout)
     def _hot_params(self):
@@ -245,8 +251,14 @@ class TalkingFace(nn.Module):
     def rgb_forward(self, uv_audio_pts, time_pts=None, head_pose_pts=None, rgb_pts=None, lms_pts=None, text_pts=None):
         """tf_nerf.py:225-285.  uv_audio_pts [N, uv_dims+64]; time_pts: only element 0 is used (tf_nerf.py:439)."""
         if self._needs_grad(uv_audio_pts):
+            x = uv_audio_pts
+            if (self.train_precision == "bf16" and isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and self.uv_dims == 2
+                    and self.output_ch == 3 and x.shape[1] == 66 and x.shape[0] >= self.dropin_min_rows and R.rows_constant(x, 2, 64)):
+                # opt-in: the call's rows share one latent (training.py:216-233) -> bf16 tensor-core forward / backward
+                from .autograd import rgb_forward_train_tc
+                return rgb_forward_train_tc(self, x, time_pts)
             t = None if time_pts is None else int(torch.as_tensor(time_pts).reshape(-1)[0].item())
-            from .autograd import rgb_forward_train      # fused fp32 forward (saves activations) + fused dgrad kernel
+            from .autograd import rgb_forward_train      # exact fp32: fused forward (saves activations) + fused dgrad kernel
             return rgb_forward_train(self, uv_audio_pts, t)
         x = uv_audio_pts
         if isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and x.shape[1] == self.uv_dims + 64:
