@@ -233,6 +233,17 @@ int32_t s2l_train_rows_fwd(const void* blob, const float* x, int64_t n_rows, con
 int32_t s2l_train_rows_bwd(const void* blob, const float* d_out, const float* x, int64_t n_rows, const int64_t* time_idx_dev,
                            const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream);
 
+/* The GEMMs of the exact fp32 per-call backward (autograd through tf_nerf.py:252-283, loss.backward() training.py:559):
+ *   s2l_wgrad_rows_fp32: out[l] [A,B] = dy[l]^T h[l] for n_mats matrices, dy[l] [N,A] / h[l] [N,B] row-major, matrix l at
+ *                        dy + l*mat_stride_dy / h + l*mat_stride_h (a stride of 0 shares one operand between the matrices);
+ *                        split over the rows, partials in scratch (s2l_wgrad_rows_scratch_bytes), summed in a fixed order.
+ *   s2l_dx_rows_fp32:    out [N,b_dim] (row stride ld_out) = a1 [N,256] w1 [256,b_dim] (+ a2 w2 when a2 != NULL).  */
+size_t  s2l_wgrad_rows_scratch_bytes(int64_t n_rows, int32_t n_mats, int32_t a_dim, int32_t b_dim);
+int32_t s2l_wgrad_rows_fp32(const float* dy, const float* h, int64_t n_rows, int32_t n_mats, int32_t a_dim, int32_t b_dim,
+                            int64_t mat_stride_dy, int64_t mat_stride_h, float* out, void* scratch, void* stream);
+int32_t s2l_dx_rows_fp32(const float* a1, const float* w1, const float* a2, const float* w2, int64_t n_rows, int32_t b_dim,
+                         float* out, int32_t ld_out, void* stream);
+
 /* Replaces: Embedder.__call__ (tf_nerf.py:404-425): x rows (first uv_dims floats of each row_stride-float row) -> pe [N,E]. */
 int32_t s2l_embed_fwd(const float* x, int64_t n_rows, int32_t row_stride, int32_t uv_dims, float* pe, void* stream);
 

@@ -1,8 +1,9 @@
 """Training path of TalkingFace.rgb_forward: a torch.autograd.Function whose forward is the fused fp32 kernel
 (s2l_rgb_forward_rows_train, saves 10 activation tensors) and whose backward is the fused data-gradient kernel
-(s2l_mlp_bwd_rows) followed by plain library GEMMs for the weight gradients (dW_l = dPre_l^T h_{l-1}) and
-the per-row latent gradient.  Replaces autograd through tf_nerf.py:225-285 (loss.backward(), training.py:559).
-SURVEY §8(f) rank 2 — first step: exact fp32 arithmetic; a tensor-core dgrad/wgrad is future work."""
+(s2l_mlp_bwd_rows) followed by the library's own fp32 GEMM kernels for the weight gradients (dW_l = dPre_l^T h_{l-1},
+s2l_wgrad_rows_fp32) and the per-row latent / coordinate gradient (s2l_dx_rows_fp32) — no torch GEMM on the path.
+Replaces autograd through tf_nerf.py:225-285 (loss.backward(), training.py:559) in exact fp32 arithmetic; the tensor-core
+(bf16) training paths are FusedLipRender and FusedMLPRowsTC below."""
 import ctypes as C
 
 import torch
@@ -18,20 +19,17 @@ def param_order():
     return [n + s for n in _W_ORDER for s in (".weight", ".bias")]
 
 
-def _wgrad(dy, h):
-    """sum_n dy[l,n,:]^T h[l,n,:] for a stack of layers: [L,N,A] x [L,N,B] -> [L,A,B].  A [256,N] x [N,256] product has only
-    four 128x128 output tiles — far too few for 148 SMs — so the reduction over N is split into S slabs that run as
-    extra batch entries of ONE bmm and are summed afterwards (split-K, deterministic)."""
-    L, N = dy.shape[0], dy.shape[1]
-    S = max(1, min(16, N // 512))
-    n_main = (N // S) * S
-    if S == 1 or n_main == 0:
-        return torch.bmm(dy.transpose(1, 2), h)
-    a = dy[:, :n_main].reshape(L * S, n_main // S, dy.shape[2])
-    b = h[:, :n_main].reshape(L * S, n_main // S, h.shape[2])
-    out = torch.bmm(a.transpose(1, 2), b).view(L, S, dy.shape[2], h.shape[2]).sum(1)
-    if n_main < N:
-        out = out + torch.bmm(dy[:, n_main:].transpose(1, 2), h[:, n_main:])
+def _wgrad(dy, h, L, stride_dy, stride_h):
+    """out[l] = dy_l^T h_l for L matrices: dy_l [N,A] at dy + l*stride_dy floats, h_l [N,B] at h + l*stride_h floats (a stride of
+    0 shares the operand) -> [L,A,B].  dy / h are the FIRST matrices (contiguous [N,A] / [N,B] views).  One launch of the
+    library's split-K fp32 kernel (partials summed in a fixed order: deterministic)."""
+    lib = _cabi.lib()
+    N, A, B = dy.shape[0], dy.shape[1], h.shape[1]
+    assert dy.is_contiguous() and h.is_contiguous() and h.shape[0] == N
+    out = torch.empty(L, A, B, device=dy.device)
+    scratch = torch.empty(max(16, lib.s2l_wgrad_rows_scratch_bytes(N, L, A, B)), dtype=torch.uint8, device=dy.device)
+    _cabi.check(lib.s2l_wgrad_rows_fp32(_ptr(dy), _ptr(h), N, L, A, B, stride_dy, stride_h, _ptr(out), _ptr(scratch), _stream()),
+                "s2l_wgrad_rows_fp32")
     return out
 
 
@@ -56,6 +54,11 @@ class FusedMLPRows(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            return FusedMLPRows._backward(ctx, d_out)
+
+    @staticmethod
+    def _backward(ctx, d_out):
         lib = _cabi.lib()
         x, acts, *params = ctx.saved_tensors
         P = dict(zip(param_order(), params))
@@ -70,30 +73,30 @@ class FusedMLPRows(torch.autograd.Function):
                                              _stream()), "s2l_mlp_bwd_rows")
             _cabi.check(lib.s2l_embed_fwd(_ptr(x), N, x.shape[1], D, _ptr(pe), _stream()), "s2l_embed_fwd")
         d_net, d_skip = dsave[0], dsave[6]
-        lat = x[:, D:]
+        lat = x[:, D:].contiguous()
         g = {}
-        # ---- weight gradients: plain GEMMs over the saved / produced [N,256] buffers
-        g["output_linear.weight"] = _wgrad(d_out[None], acts[9:10])[0]
+        mat = N * 256                                                        # floats between consecutive [N,256] buffers
+        # ---- weight gradients: the library's fp32 split-K GEMM over the saved / produced [N,256] buffers
+        g["output_linear.weight"] = _wgrad(d_out, acts[9], 1, 0, 0)[0]
         g["output_linear.bias"] = d_out.sum(0)
         # dsave rows: 0 d_net, 1-5 dPre of layers 0-4, 6 d_skip, 7-9 dPre of layers 5-7;  acts rows: 0-4 inputs of layers 0-4,
         # 5 h4 / 6 h_skip (the two halves of layer 5's input), 7-8 inputs of layers 6-7, 9 input of output_linear.
         # Same-shape products are batched (the step is launch-bound at the reference's 9 600-row calls).
         col = dsave.sum(1)                                                   # every bias gradient in one reduction [10,256]
-        w04 = _wgrad(dsave[1:6], acts[0:5])                                  # layers 0-4
-        w67 = _wgrad(dsave[8:10], acts[7:9])                                 # layers 6-7
-        w5 = _wgrad(dsave[7:8].expand(2, -1, -1), torch.stack([acts[6], acts[5]]))   # [h_skip | h4]
+        w04 = _wgrad(dsave[1], acts[0], 5, mat, mat)                         # layers 0-4
+        w67 = _wgrad(dsave[8], acts[7], 2, mat, mat)                         # layers 6-7
+        w5 = _wgrad(dsave[7], acts[5], 2, 0, mat)                            # layer 5 against (h4, h_skip)
         for l in range(5):
             g["pts_linears.%d.weight" % l] = w04[l]
             g["pts_linears.%d.bias" % l] = col[1 + l]
-        g["pts_linears.5.weight"] = torch.cat([w5[0], w5[1]], 1)
+        g["pts_linears.5.weight"] = torch.cat([w5[1], w5[0]], 1)            # input order of layer 5: [h_skip | h4]
         g["pts_linears.5.bias"] = col[7]
         for i, l in enumerate((6, 7)):
             g["pts_linears.%d.weight" % l] = w67[i]
             g["pts_linears.%d.bias" % l] = col[8 + i]
         s_net, s_skip = col[0], col[6]
-        both = torch.stack([d_net, d_skip])                                  # [2,N,256]
-        wuv = _wgrad(both, pe[None].expand(2, -1, -1))                       # fc_uv / fc_uv_skip
-        wau = _wgrad(both, lat[None].expand(2, -1, -1))                      # fc_audio / fc_audio_skip
+        wuv = _wgrad(d_net, pe, 2, 6 * mat, 0)                               # fc_uv / fc_uv_skip (d_net = dsave[0], d_skip = dsave[6])
+        wau = _wgrad(d_net, lat, 2, 6 * mat, 0)                              # fc_audio / fc_audio_skip
         g["fc_uv.weight"], g["fc_uv_skip.weight"] = wuv[0], wuv[1]
         g["fc_audio.weight"], g["fc_audio_skip.weight"] = wau[0], wau[1]
         for n, s in (("fc_uv", s_net), ("fc_audio", s_net), ("fc_uv_skip", s_skip), ("fc_audio_skip", s_skip)):
@@ -101,8 +104,8 @@ class FusedMLPRows(torch.autograd.Function):
         if ctx.time_idx is not None:
             ang = torch.tensor(float(ctx.time_idx), device=x.device) * ctx.div_term            # tf_nerf.py:439-440
             tpe = torch.stack([torch.sin(ang), torch.cos(ang)], 1).reshape(-1)
-            g["fc_time.weight"] = torch.outer(s_net, tpe)
-            g["fc_time_skip.weight"] = torch.outer(s_skip, tpe)
+            g["fc_time.weight"] = s_net[:, None] * tpe[None, :]
+            g["fc_time_skip.weight"] = s_skip[:, None] * tpe[None, :]
             g["fc_time.bias"], g["fc_time_skip.bias"] = s_net, s_skip
         else:
             for n in ("fc_time", "fc_time_skip"):
@@ -113,8 +116,12 @@ class FusedMLPRows(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            dx[:, D:] = d_net @ P["fc_audio.weight"] + d_skip @ P["fc_audio_skip.weight"]
-            d_pe = d_net @ P["fc_uv.weight"] + d_skip @ P["fc_uv_skip.weight"]              # [N, D + 20 D]
+            d_pe = torch.empty(N, E, device=x.device)                                         # [N, D + 20 D]
+            wts = [P[n + ".weight"].detach().contiguous().float() for n in ("fc_audio", "fc_audio_skip", "fc_uv", "fc_uv_skip")]
+            _cabi.check(lib.s2l_dx_rows_fp32(_ptr(d_net), _ptr(wts[0]), _ptr(d_skip), _ptr(wts[1]), N, 64,
+                                             dx.data_ptr() + 4 * D, D + 64, _stream()), "s2l_dx_rows_fp32")
+            _cabi.check(lib.s2l_dx_rows_fp32(_ptr(d_net), _ptr(wts[2]), _ptr(d_skip), _ptr(wts[3]), N, E, _ptr(d_pe), E, _stream()),
+                        "s2l_dx_rows_fp32")
             freqs = (2.0 ** torch.arange(10, device=x.device, dtype=torch.float32))          # 2**linspace(0, 9, 10)
             ang = x[:, None, :D] * freqs[None, :, None]                                       # [N, 10, D]
             blocks = d_pe[:, D:].reshape(N, 10, 2, D)                                         # per frequency: (sin block, cos block)
