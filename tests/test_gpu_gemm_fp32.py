@@ -25,7 +25,7 @@ def test_wgrad_rows_matches_float64(N, L, A, B, share):
                                        scratch.data_ptr(), s), "wgrad")
     ref = torch.einsum("lna,lnb->lab", dy.double(), h.double().expand(L, -1, -1))
     scale = ref.abs().max().item()
-    assert (out.double() - ref).abs().max().item() <= 2e-6 * scale * max(1.0, (N / 1000) ** 0.5)
+    assert (out.double() - ref).abs().max().item() <= 1e-5 * scale      # fp32 sums of N terms, slab-wise
     out2 = torch.empty_like(out)
     cabi.check(lib.s2l_wgrad_rows_fp32(dy.data_ptr(), h.data_ptr(), N, L, A, B, N * A, 0 if share else N * B, out2.data_ptr(),
                                        scratch.data_ptr(), s), "wgrad")
