@@ -204,7 +204,11 @@ def post_fusion_extras(dev, B=64, h=500, w=500, lh=80, lw=120, x0=190, y0=300):
             e1.record(); e1.synchronize()
             return e0.elapsed_time(e1) / n
         ms = timeit(lambda: s2l.post_fusion_compose(lip, face, gt, mask, coord, x0, y0, True, lw // 5, want_canonical=False))
-        alg = B * (h * w * (8 + 12 + 12) + h * w * 12 + h * w * 12 + lh * lw * 12)      # coord + gt + out, face, mask, lip: unique bytes
+        # unique bytes the result depends on: coord + gt + out for every pixel; face and mask only under the warped (expanded)
+        # lip rectangle (tf_nerf.py:354-363) — elsewhere the output is the ground-truth pixel; the lip crop
+        pad = lw // 5
+        rect = (lh + 3 * pad) * (lw + 2 * pad)
+        alg = B * (h * w * (8 + 12 + 12) + rect * 12 + rect * 12 + lh * lw * 12)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -12,15 +12,46 @@ namespace s2l {
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.02f * x; }
 constexpr int kAudioSave = 256 + 128 + 128 + 64 + 64;      // x1 [32][8] | x2 [32][4] | x3 [64][2] | x4 [64] | x5 [64]
 
-// out[o][t] = b[o] + sum_c sum_j w[o][c][j] * in[c][2t-1+j], zero padded; in/out in shared memory
-template <int CIN, int COUT, int TIN>
-__device__ __forceinline__ void conv_k3s2(const float* __restrict__ w, const float* __restrict__ b,
-                                          const float* in, float* out, int tid, int nthreads) {
+// AudioNet's weights are staged ONCE per CTA into shared memory (4-byte cp.async, every copy in flight at once, one commit group
+// per layer) with an odd row stride so that threads owning different output channels hit different banks.  A single row's
+// encode used to be a chain of ~290 dependent-latency global loads (57 us with the blob cold in L2 — the drop-in caller's
+// 121 MB tiled window evicts it every frame); staged, it is one HBM round trip plus ~3 us of shared-memory FMAs.
+constexpr int kWs0 = 29 * 3, kWs1 = 32 * 3 + 1, kWs2 = 32 * 3 + 1, kWs3 = 64 * 3 + 1, kWsF = 64 + 1;   // padded row strides
+constexpr int S_CONV0_W = 0, S_CONV0_B = S_CONV0_W + 32 * kWs0;
+constexpr int S_CONV1_W = S_CONV0_B + 32, S_CONV1_B = S_CONV1_W + 32 * kWs1;
+constexpr int S_CONV2_W = S_CONV1_B + 32, S_CONV2_B = S_CONV2_W + 64 * kWs2;
+constexpr int S_CONV3_W = S_CONV2_B + 64, S_CONV3_B = S_CONV3_W + 64 * kWs3;
+constexpr int S_FC1_W = S_CONV3_B + 64, S_FC1_B = S_FC1_W + 64 * kWsF;
+constexpr int S_FC2_W = S_FC1_B + 64, S_FC2_B = S_FC2_W + 64 * kWsF;
+constexpr int S_TOTAL = S_FC2_B + 64;
+constexpr size_t kAudioSmemBytes = (size_t)S_TOTAL * sizeof(float);
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// one layer: weight rows [ROWS][K] -> stride KS in shared memory, then the bias; one commit group
+template <int ROWS, int K, int KS>
+__device__ __forceinline__ void stage_layer(float* sw, float* sb, const float* __restrict__ gw, const float* __restrict__ gb, int tid) {
+  for (int i = tid; i < ROWS * K; i += 256) cp_async4(sw + (i / K) * KS + (i % K), gw + i);
+  for (int i = tid; i < ROWS; i += 256) cp_async4(sb + i, gb + i);
+  cp_async_commit();
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// out[o][t] = b[o] + sum_c sum_j w[o][c][j] * in[c][2t-1+j], zero padded; in/out (and here w, b) in shared memory
+template <int CIN, int COUT, int TIN, int WS>
+__device__ __forceinline__ void conv_k3s2(const float* w, const float* b, const float* in, float* out, int tid, int nthreads) {
   constexpr int TOUT = TIN / 2;
   for (int idx = tid; idx < COUT * TOUT; idx += nthreads) {
     const int o = idx / TOUT, t = idx % TOUT;
     float acc = 0.f;
-    const float* wo = w + o * CIN * 3;
+    const float* wo = w + o * WS;
+#pragma unroll 4
     for (int c = 0; c < CIN; ++c) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -32,7 +63,7 @@ __device__ __forceinline__ void conv_k3s2(const float* __restrict__ w, const flo
   }
 }
 
-__global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __restrict__ blob, Layout L,
+__global__ void __launch_bounds__(256, 1) audio_encode_kernel(const uint8_t* __restrict__ blob, Layout L,
                                                            const float* __restrict__ audio, int transposed,
                                                            const long long* __restrict__ frame_idx,
                                                            float* __restrict__ latent, float* __restrict__ frame_bias,
@@ -46,10 +77,41 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
   __shared__ float x1[32 * 8], x2[32 * 4], x3[64 * 2], x4[64], x5[64], lat[64];
   __shared__ float pe[kTimePE];
   __shared__ float b0s[256], bss[256];
+  extern __shared__ __align__(16) float Ws[];           // AudioNet weights, padded rows (S_* offsets)
   const int tid = threadIdx.x;
-  const bool bcast = gate_flag && *gate_flag == 0;      // every row equals row 0 (the drop-in's tiled window, inference.py:144)
-  (void)lat0;
-  for (int f = bcast ? 0 : blockIdx.x; f < (bcast ? 1 : n_frames); f += gridDim.x) {
+  if (gate_flag && *gate_flag == 0) {
+    // every row equals row 0 (the drop-in's tiled window, inference.py:144), which a one-CTA launch has just encoded
+    // into lat0: broadcast it over this CTA's share of the rows
+    if ((reinterpret_cast<uintptr_t>(latent) & 15) == 0) {
+      const float4 v = reinterpret_cast<const float4*>(lat0)[tid & (kLatent / 4 - 1)];     // 256 % 16 == 0: a thread's column never changes
+      float4* out4 = reinterpret_cast<float4*>(latent);
+      for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < (long long)n_frames * (kLatent / 4); i += (long long)gridDim.x * blockDim.x)
+        out4[i] = v;
+    } else {
+      for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < (long long)n_frames * kLatent; i += (long long)gridDim.x * blockDim.x)
+        latent[i] = lat0[i & (kLatent - 1)];
+    }
+    return;
+  }
+  if (blockIdx.x >= n_frames) return;
+  if (frame_bias) {
+    // the per-frame-constant weights (fc_audio / fc_time rows, W0 / W5 columns: 640 KB) are usually cold: start them towards L2
+    const char* p0 = reinterpret_cast<const char*>(C + C_FCA_WT);
+    const char* p1 = reinterpret_cast<const char*>(C + C_FCAS_WT);
+    for (int i = tid; i < 64 * 256 * 4 / 128; i += 256) { prefetch_l2(p0 + i * 128); prefetch_l2(p1 + i * 128); }
+    const char* q0 = reinterpret_cast<const char*>(Fp + f_pts_off(0));
+    const char* q5 = reinterpret_cast<const char*>(Fp + f_pts_off(5));
+    for (int i = tid; i < 256 * 256 * 4 / 128; i += 256) { prefetch_l2(q0 + i * 128); prefetch_l2(q5 + i * 128); }
+  }
+  if (!latent_in) {
+    stage_layer<32, 29 * 3, kWs0>(Ws + S_CONV0_W, Ws + S_CONV0_B, A + A_CONV0_W, A + A_CONV0_B, tid);
+    stage_layer<32, 32 * 3, kWs1>(Ws + S_CONV1_W, Ws + S_CONV1_B, A + A_CONV1_W, A + A_CONV1_B, tid);
+    stage_layer<64, 32 * 3, kWs2>(Ws + S_CONV2_W, Ws + S_CONV2_B, A + A_CONV2_W, A + A_CONV2_B, tid);
+    stage_layer<64, 64 * 3, kWs3>(Ws + S_CONV3_W, Ws + S_CONV3_B, A + A_CONV3_W, A + A_CONV3_B, tid);
+    stage_layer<64, 64, kWsF>(Ws + S_FC1_W, Ws + S_FC1_B, A + A_FC1_W, A + A_FC1_B, tid);
+    stage_layer<64, 64, kWsF>(Ws + S_FC2_W, Ws + S_FC2_B, A + A_FC2_W, A + A_FC2_B, tid);
+  }
+  for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
   __syncthreads();                 // the previous frame's shared-memory state is no longer read
   if (tid < 10) {
     float s = 0.f, c = 1.f;
@@ -73,27 +135,35 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     // tf_nerf.py:203-207: [B,16,29] is permuted to [B,29,16]; a tensor whose last dim is 16 is used as is
     x0[i] = transposed ? a[c * kAudioWin + t] : a[t * kAudioFeat + c];
   }
+  cp_async_wait<5>();              // (each wait is immediate from the CTA's second frame on)
   __syncthreads();
-  conv_k3s2<29, 32, 16>(A + A_CONV0_W, A + A_CONV0_B, x0, x1, tid, 256);
+  conv_k3s2<29, 32, 16, kWs0>(Ws + S_CONV0_W, Ws + S_CONV0_B, x0, x1, tid, 256);
+  cp_async_wait<4>();
   __syncthreads();
-  conv_k3s2<32, 32, 8>(A + A_CONV1_W, A + A_CONV1_B, x1, x2, tid, 256);
+  conv_k3s2<32, 32, 8, kWs1>(Ws + S_CONV1_W, Ws + S_CONV1_B, x1, x2, tid, 256);
+  cp_async_wait<3>();
   __syncthreads();
-  conv_k3s2<32, 64, 4>(A + A_CONV2_W, A + A_CONV2_B, x2, x3, tid, 256);
+  conv_k3s2<32, 64, 4, kWs2>(Ws + S_CONV2_W, Ws + S_CONV2_B, x2, x3, tid, 256);
+  cp_async_wait<2>();
   __syncthreads();
-  conv_k3s2<64, 64, 2>(A + A_CONV3_W, A + A_CONV3_B, x3, x4, tid, 256);
+  conv_k3s2<64, 64, 2, kWs3>(Ws + S_CONV3_W, Ws + S_CONV3_B, x3, x4, tid, 256);
+  cp_async_wait<1>();
   __syncthreads();
   if (tid < 64) {
     float acc = 0.f;
-    for (int k = 0; k < 64; ++k) acc = fmaf(A[A_FC1_W + tid * 64 + k], x4[k], acc);
-    x5[tid] = lrelu(acc + A[A_FC1_B + tid]);
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) acc = fmaf(Ws[S_FC1_W + tid * kWsF + k], x4[k], acc);
+    x5[tid] = lrelu(acc + Ws[S_FC1_B + tid]);
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (tid < 64) {
     float acc = 0.f;
-    for (int k = 0; k < 64; ++k) acc = fmaf(A[A_FC2_W + tid * 64 + k], x5[k], acc);
-    const float v = acc + A[A_FC2_B + tid];
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) acc = fmaf(Ws[S_FC2_W + tid * kWsF + k], x5[k], acc);
+    const float v = acc + Ws[S_FC2_B + tid];
     lat[tid] = v;
-    if (latent && !bcast) latent[(size_t)f * kLatent + tid] = v;
+    if (latent) latent[(size_t)f * kLatent + tid] = v;
   }
   if (save) {      // training forward: the post-LeakyReLU activations the backward kernel needs (x1 | x2 | x3 | x4 | x5)
     float* sv = save + (size_t)f * kAudioSave;
@@ -102,27 +172,22 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     if (tid < 64) { sv[512 + tid] = x4[tid]; sv[576 + tid] = x5[tid]; }
   }
   __syncthreads();
-  if (bcast) {
-    // every CTA has just encoded row 0 itself (67 k MAC, cheaper than a second launch): broadcast it over its share of rows
-    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < (long long)n_frames * kLatent; i += (long long)gridDim.x * blockDim.x)
-      latent[i] = lat[i & (kLatent - 1)];
-    return;
-  }
   }
   if (!frame_bias) continue;
   {
     // bias0 = b_uv + (Wa a + b_a) + (Wt t + b_t)   (tf_nerf.py:252-258, same association order)
     const int n = tid;
     float ta = 0.f, tas = 0.f, tt = 0.f, tts = 0.f;
-    for (int k0 = 0; k0 < 64; k0 += 16) {
-      float wa[16], ws[16];
+    // (loads are issued in deep batches ahead of their FMAs — the weights are usually cold; the summation order is unchanged)
+    for (int k0 = 0; k0 < 64; k0 += 32) {
+      float wa[32], ws[32];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < 32; ++u) {
         wa[u] = __ldg(C + C_FCA_WT + (k0 + u) * 256 + n);
         ws[u] = __ldg(C + C_FCAS_WT + (k0 + u) * 256 + n);
       }
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < 32; ++u) {
         ta = fmaf(wa[u], lat[k0 + u], ta);
         tas = fmaf(ws[u], lat[k0 + u], tas);
       }
@@ -130,9 +195,16 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     float b0 = C[C_BIAS6 + 0 * 256 + n] + (ta + C[C_BIAS6 + 1 * 256 + n]);
     float bs = C[C_BIAS6 + 3 * 256 + n] + (tas + C[C_BIAS6 + 4 * 256 + n]);
     if (frame_idx) {
+      float wt[kTimePE], wts[kTimePE];
+#pragma unroll
       for (int k = 0; k < kTimePE; ++k) {
-        tt = fmaf(C[C_FCT_WT + k * 256 + n], pe[k], tt);
-        tts = fmaf(C[C_FCTS_WT + k * 256 + n], pe[k], tts);
+        wt[k] = __ldg(C + C_FCT_WT + k * 256 + n);
+        wts[k] = __ldg(C + C_FCTS_WT + k * 256 + n);
+      }
+#pragma unroll
+      for (int k = 0; k < kTimePE; ++k) {
+        tt = fmaf(wt[k], pe[k], tt);
+        tts = fmaf(wts[k], pe[k], tts);
       }
       b0 += (tt + C[C_BIAS6 + 2 * 256 + n]);
       bs += (tts + C[C_BIAS6 + 5 * 256 + n]);
@@ -150,17 +222,18 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
     const float* W0T = Fp + f_pts_off(0);
     const float* W5T = Fp + f_pts_off(5);
     // (the blob is often cold here — a drop-in caller's 121 MB tiled window evicts it from L2 between frames — so the 2 x 256
-    //  loads are issued 16 deep per matrix instead of one dependent pair per iteration; the summation order is unchanged)
+    //  loads are issued 64 deep per matrix instead of one dependent pair per iteration; the summation order is unchanged)
     double a0 = 0.0, a5 = 0.0;
-    for (int k0 = 0; k0 < 256; k0 += 16) {
-      float w0[16], w5[16];
+    for (int k0 = 0; k0 < 256; k0 += 64) {
+      float w0[64], w5[64];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < 64; ++u) {
         w0[u] = __ldg(W0T + (k0 + u) * 256 + n);
         w5[u] = __ldg(W5T + (k0 + u) * 256 + n);
       }
+      asm volatile("" ::: "memory");     // keep the whole batch of loads ahead of the first use
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < 64; ++u) {
         a0 += (double)w0[u] * (double)b0s[k0 + u];
         a5 += (double)w5[u] * (double)bss[k0 + u];
       }
@@ -176,6 +249,11 @@ __global__ void __launch_bounds__(256) audio_encode_kernel(const uint8_t* __rest
 
 using namespace s2l;
 
+// dynamic shared memory of the kernel when it runs AudioNet (none when the caller supplies the latent)
+static bool audio_smem_opt_in() {
+  return cudaFuncSetAttribute(audio_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAudioSmemBytes) == cudaSuccess;
+}
+
 extern "C" int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, int32_t transposed,
                                         const int64_t* frame_idx, float* latent, float* frame_bias,
                                         int32_t n_frames, int32_t uv_dims, int32_t out_ch, void* stream) {
@@ -184,7 +262,8 @@ extern "C" int32_t s2l_audio_encode_fwd(const void* blob, const float* audio, in
   if (!blob || !audio) { set_error("s2l_audio_encode_fwd: null blob/audio"); return 1; }
   if (n_frames < 0) { set_error("s2l_audio_encode_fwd: negative n_frames"); return 2; }
   if (n_frames == 0) return 0;
-  audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  if (!audio_smem_opt_in()) { set_error("s2l_audio_encode_fwd: cannot opt in to %zu bytes of shared memory", kAudioSmemBytes); return 5; }
+  audio_encode_kernel<<<n_frames, 256, kAudioSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed,
       reinterpret_cast<const long long*>(frame_idx), latent, frame_bias, nullptr, 0, n_frames, nullptr, nullptr);
   return check_launch("audio_encode_kernel") ? 0 : 5;
@@ -215,14 +294,36 @@ __global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __rest
   const int nv = ncols / VW;
   const V* r0 = reinterpret_cast<const V*>(x + col0);
   bool diff = false;
-  for (long long r = warp + 1; r < n_rows; r += n_warps) {
-    const V* rr = reinterpret_cast<const V*>(x + r * row_stride + col0);
-    for (int j = lane; j < nv; j += 32) {
-      const V a = rr[j], b = __ldg(r0 + j);
-      const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-      const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+  auto ne = [](const V& a, const V& b) {
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+    bool d = false;
 #pragma unroll
-      for (int t = 0; t < VW; ++t) diff |= pa[t] != pb[t];
+    for (int t = 0; t < VW; ++t) d |= pa[t] != pb[t];
+    return d;
+  };
+  if (nv <= 128) {
+    // a lane owns up to 4 words of the row: row 0's copies stay in registers and two rows (8 loads per lane) are in flight at
+    // once — the 121 MB tiled window of the drop-in caller streams at HBM rate instead of one dependent load per lane
+    V ref[4], a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ref[q] = (lane + 32 * q < nv) ? __ldg(r0 + lane + 32 * q) : V{};
+    for (long long r = 2 * warp + 1; r < n_rows; r += 2 * n_warps) {
+      const V* ra = reinterpret_cast<const V*>(x + r * row_stride + col0);
+      const V* rb = reinterpret_cast<const V*>(x + (r + 1) * row_stride + col0);
+      const bool two = r + 1 < n_rows;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = (lane + 32 * q < nv) ? ra[lane + 32 * q] : ref[q];
+        b[q] = (two && lane + 32 * q < nv) ? rb[lane + 32 * q] : ref[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) diff |= ne(a[q], ref[q]) | ne(b[q], ref[q]);
+    }
+  } else {
+    for (long long r = warp + 1; r < n_rows; r += n_warps) {
+      const V* rr = reinterpret_cast<const V*>(x + r * row_stride + col0);
+      for (int j = lane; j < nv; j += 32) diff |= ne(rr[j], __ldg(r0 + j));
     }
   }
   if (__syncthreads_or(diff) && threadIdx.x == 0) atomicExch(flag, 1);
@@ -236,7 +337,7 @@ extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_s
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
   if (n_rows <= 1 || ncols == 0) return 0;
-  const long long want = (n_rows + 7) / 8;                                   // 8 warps per block, one row per warp per pass
+  const long long want = (n_rows + 15) / 16;                                 // 8 warps per block, two rows per warp per pass
   const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
   const bool wide = (row_stride % 2 == 0) && (col0 % 2 == 0) && (ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const bool wide4 = (row_stride % 4 == 0) && (col0 % 4 == 0) && (ncols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -261,8 +362,12 @@ extern "C" int32_t s2l_audio_merge_auto(const void* blob, const float* audio, in
   int rc = s2l_rows_differ(audio, n_rows, kAudioWin * kAudioFeat, 0, kAudioWin * kAudioFeat, flag, stream);
   if (rc) return rc;
   const uint8_t* b = reinterpret_cast<const uint8_t*>(blob);
-  const int grid = (int)(n_rows < 148 * 4 ? n_rows : 148 * 4);
-  audio_encode_kernel<<<grid, 256, 0, st>>>(b, blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, (int)n_rows, flag, lat0);
+  if (!audio_smem_opt_in()) { set_error("s2l_audio_merge_auto: cannot opt in to %zu bytes of shared memory", kAudioSmemBytes); return 5; }
+  // row 0 -> lat0 (one CTA, unconditional), then either a broadcast of lat0 (flag 0) or an encode of every row (flag 1)
+  audio_encode_kernel<<<1, 256, kAudioSmemBytes, st>>>(b, blob_layout(), audio, transposed, nullptr, lat0, nullptr, nullptr, 0, 1, nullptr, nullptr);
+  if (!check_launch("audio_encode_kernel(row 0)")) return 5;
+  const int grid = (int)(n_rows < 148 ? n_rows : 148);                        // one CTA per SM (the staged weights fill its shared memory)
+  audio_encode_kernel<<<grid, 256, kAudioSmemBytes, st>>>(b, blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, (int)n_rows, flag, lat0);
   return check_launch("audio_encode_kernel(auto)") ? 0 : 5;
 }
 
@@ -390,7 +495,8 @@ extern "C" int32_t s2l_audio_train_fwd(const void* blob, const float* audio, int
   if (!blob || (n_frames > 0 && (!audio || !latent || !save))) { set_error("s2l_audio_train_fwd: null argument"); return 1; }
   if (n_frames < 0) { set_error("s2l_audio_train_fwd: negative n_frames"); return 2; }
   if (n_frames == 0) return 0;
-  audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  if (!audio_smem_opt_in()) { set_error("s2l_audio_train_fwd: cannot opt in to %zu bytes of shared memory", kAudioSmemBytes); return 5; }
+  audio_encode_kernel<<<n_frames, 256, kAudioSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(blob), blob_layout(), audio, transposed, nullptr, latent, nullptr, nullptr, 0, n_frames, nullptr,
       nullptr, save);
   return check_launch("audio_encode_kernel(train)") ? 0 : 5;

@@ -36,16 +36,19 @@ __device__ __forceinline__ float merged_canon(const PfArgs& a, int b, int cy, in
 
 // grid = (pixel blocks, batch): no 64-bit division per thread; 32-bit offsets inside a frame (an image plane is < 2^31 bytes);
 // the four taps share one base offset.  ncu on the first version: sm__throughput 73 %, DRAM 30 % — the kernel was
-// instruction-bound (611 warp-instructions per 32 pixels, mostly index arithmetic), not memory-bound.
-__device__ __forceinline__ void pf_pixel_direct(const PfArgs& a, int b, int pix) {
-  const int npix = a.Hf * a.Wf;
+// instruction-bound (611 warp-instructions per 32 pixels, mostly index arithmetic), not memory-bound.  Second capture
+// (profiles/r2h): 482 instructions per warp, issue slots 71 % busy, L1 41 %, DRAM 2.9 TB/s — still issue-bound, and ~90 % of
+// the pixels of a 500x500 frame lie outside the warped lip mask, where the result is the ground-truth pixel.  So the warped
+// mask is evaluated FIRST (analytically in the rectangle mode, from the 12 mask taps otherwise) and a pixel whose mask is
+// zero in every channel returns before any face / lip / mask gather: bit-identical output (the blend is a select on
+// mask != 0), ~8x fewer instructions for those pixels, and face / mask are only read around the lip.
+// one observed pixel: g = its sampling coordinate, gtv = its ground-truth colour -> out[3]
+template <bool RECT>
+__device__ __forceinline__ void pf_pixel_value(const PfArgs& a, int b, float2 g, const float (&gtv)[3], float (&out)[3]) {
   const size_t canon = (size_t)b * a.h * a.w * 3;
   const float* __restrict__ face = a.face + canon;
   const float* __restrict__ mask = a.mask + canon;
   const float* __restrict__ lip = a.lip + (size_t)b * a.lh * a.lw * 3;
-  const float2 g = reinterpret_cast<const float2*>(a.coord)[(size_t)b * npix + pix];
-  const float* __restrict__ gtp = a.gt + ((size_t)b * npix + pix) * 3;
-  const float gt0 = __ldg(gtp), gt1 = __ldg(gtp + 1), gt2 = __ldg(gtp + 2);
   // grid_sampler_unnormalize, align_corners=False: ((coord + 1) * size - 1) / 2
   const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.x, 1.f), (float)a.w), 1.f), 0.5f);
   const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.y, 1.f), (float)a.h), 1.f), 0.5f);
@@ -69,39 +72,91 @@ __device__ __forceinline__ void pf_pixel_direct(const PfArgs& a, int b, int pix)
   const bool rx0 = x0 >= a.rx0 && x0 < a.rx1, rx1 = x0 + 1 >= a.rx0 && x0 + 1 < a.rx1;
   const bool ry0 = y0 >= a.ry0 && y0 < a.ry1, ry1 = y0 + 1 >= a.ry0 && y0 + 1 < a.ry1;
   const bool rin[4] = {ry0 && rx0, ry0 && rx1, ry1 && rx0, ry1 && rx1};
-  // every load of the pixel is issued before the first use (coord -> address -> gather is a dependent chain)
-  float mk[4][3], fc[4][3], lp[4][3];
+  // the warped mask, per channel (grid_sample of the mask: taps nw, ne, sw, se accumulated in that order)
+  float mk[4][3], macc[3] = {0.f, 0.f, 0.f};
+  if (RECT) {
+    float m = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (tin[t]) m = __fadd_rn(m, __fmul_rn(rin[t] ? 1.f : 0.f, tw[t]));
+    macc[0] = macc[1] = macc[2] = m;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) mk[t][c] = tin[t] ? __ldg(mask + toff[t] + c) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (tin[t]) macc[c] = __fadd_rn(macc[c], __fmul_rn(mk[t][c], tw[t]));
+  }
+  // mask[mask != 0] = 1 ; out = mask*merged + (1-mask)*gt      (tf_nerf.py:367-386): outside the mask the pixel is gt
+  if (macc[0] == 0.f && macc[1] == 0.f && macc[2] == 0.f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = gtv[c];
+    return;
+  }
+  // every remaining load of the pixel is issued before the first use (coord -> address -> gather is a dependent chain)
+  float fc[4][3], lp[4][3];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      mk[t][c] = tin[t] ? __ldg(mask + toff[t] + c) : 0.f;
+      if (RECT) mk[t][c] = tin[t] ? __ldg(mask + toff[t] + c) : 0.f;
       fc[t][c] = tin[t] ? __ldg(face + toff[t] + c) : 0.f;
       lp[t][c] = (tin[t] && lin[t]) ? __ldg(lip + loff[t] + c) : 0.f;
     }
   }
-  const float gtv[3] = {gt0, gt1, gt2};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float acc = 0.f, macc = 0.f;
+    float acc = 0.f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (tin[t]) {
         // merged_canonical = m*lip_pad + (1-m)*face   (tf_nerf.py:352), then the bilinear tap
         const float mc = __fadd_rn(__fmul_rn(mk[t][c], lp[t][c]), __fmul_rn(__fsub_rn(1.f, mk[t][c]), fc[t][c]));
         acc = __fadd_rn(acc, __fmul_rn(mc, tw[t]));
-        const float mv = a.rect ? (rin[t] ? 1.f : 0.f) : mk[t][c];
-        macc = __fadd_rn(macc, __fmul_rn(mv, tw[t]));
       }
     }
-    // mask[mask != 0] = 1 ; out = mask*merged + (1-mask)*gt      (tf_nerf.py:367-386)
-    a.fused[((size_t)b * 3 + c) * npix + pix] = (macc != 0.f) ? acc : gtv[c];
+    out[c] = (macc[c] != 0.f) ? acc : gtv[c];
   }
 }
 
+template <bool RECT>
 __global__ void __launch_bounds__(256) post_fusion_kernel(PfArgs a) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix < a.Hf * a.Wf) pf_pixel_direct(a, blockIdx.y, pix);
+  const int npix = a.Hf * a.Wf, b = blockIdx.y;
+  if (pix >= npix) return;
+  const float2 g = reinterpret_cast<const float2*>(a.coord)[(size_t)b * npix + pix];
+  const float* __restrict__ gtp = a.gt + ((size_t)b * npix + pix) * 3;
+  const float gtv[3] = {__ldg(gtp), __ldg(gtp + 1), __ldg(gtp + 2)};
+  float out[3];
+  pf_pixel_value<RECT>(a, b, g, gtv, out);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a.fused[((size_t)b * 3 + c) * npix + pix] = out[c];
+}
+
+// Four consecutive pixels per thread (plane size a multiple of 4, 16-byte aligned bases): the streamed operands move as
+// 2 + 3 LDG.128 and 3 STG.128 per thread, all loads issued before the first pixel is evaluated — 80 bytes in flight per
+// thread instead of 20 (the scalar kernel at 1024 threads / SM kept ~20 KB in flight per SM, half of what HBM latency needs).
+template <bool RECT>
+__global__ void __launch_bounds__(256) post_fusion_kernel4(PfArgs a) {
+  const int npix = a.Hf * a.Wf, b = blockIdx.y;
+  const int pix = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (pix >= npix) return;
+  const float4* cp = reinterpret_cast<const float4*>(a.coord + ((size_t)b * npix + pix) * 2);
+  const float4* gp = reinterpret_cast<const float4*>(a.gt + ((size_t)b * npix + pix) * 3);
+  const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+  const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+  const float2 cs[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+  const float gts[4][3] = {{g0.x, g0.y, g0.z}, {g0.w, g1.x, g1.y}, {g1.z, g1.w, g2.x}, {g2.y, g2.z, g2.w}};
+  float o[4][3];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pf_pixel_value<RECT>(a, b, cs[q], gts[q], o[q]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<float4*>(a.fused + ((size_t)b * 3 + c) * npix + pix) = make_float4(o[0][c], o[1][c], o[2][c], o[3][c]);
 }
 
 // (A tiled variant — the block stages merged_canonical of its tile's canonical bounding box in shared memory and the pixels
@@ -158,7 +213,18 @@ extern "C" int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* fa
     set_error("s2l_post_fusion_compose: image planes beyond 2^31 elements / batch beyond 65535 are not supported");
     return 2;
   }
-  post_fusion_kernel<<<dim3((unsigned)((out_h * out_w + 255) / 256), (unsigned)batch), 256, 0, st>>>(a);
+  const int npix = out_h * out_w;
+  const bool vec4 = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(coord) | reinterpret_cast<uintptr_t>(rgb_gt) |
+                                         reinterpret_cast<uintptr_t>(fused_nchw)) & 15) == 0;
+  if (vec4) {
+    const dim3 grid((unsigned)((npix / 4 + 255) / 256), (unsigned)batch);
+    if (a.rect) post_fusion_kernel4<true><<<grid, 256, 0, st>>>(a);
+    else post_fusion_kernel4<false><<<grid, 256, 0, st>>>(a);
+  } else {
+    const dim3 grid((unsigned)((npix + 255) / 256), (unsigned)batch);
+    if (a.rect) post_fusion_kernel<true><<<grid, 256, 0, st>>>(a);
+    else post_fusion_kernel<false><<<grid, 256, 0, st>>>(a);
+  }
   if (!check_launch("post_fusion_kernel")) return 5;
   if (merged_canonical) {
     const long long m = (long long)batch * face_h * face_w * 3;

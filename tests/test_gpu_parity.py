@@ -424,6 +424,29 @@ def test_post_fusion_compose_vs_golden(S, golden, case):
     assert maxabs(f2.permute(0, 2, 3, 1).cpu(), want) < 2e-6
 
 
+@pytest.mark.parametrize("Hf,Wf", [(37, 43), (40, 44)])
+@pytest.mark.parametrize("expand", [True, False])
+def test_post_fusion_scalar_and_vector_paths_vs_oracle(S, Hf, Wf, expand):
+    """The 4-pixels-per-thread kernel (plane size % 4 == 0) and the scalar kernel (odd plane) against the oracle, with a
+    strong warp (taps outside the canonical image, pixels inside / outside / on the edge of the warped mask)."""
+    g = torch.Generator().manual_seed(Hf * 100 + Wf + int(expand))
+    B, h, w, lh, lw, x0, y0 = 3, 48, 52, 10, 15, 12, 20
+    lip, face, gt = torch.rand(B, lh, lw, 3, generator=g), torch.rand(B, h, w, 3, generator=g), torch.rand(B, Hf, Wf, 3, generator=g)
+    mask = torch.zeros(B, h, w, 3)
+    mask[:, y0 + 1:y0 + lh - 1, x0 + 1:x0 + lw - 1] = 1
+    mask[:, y0 + 2, x0 + 3, 1] = 0.5                                        # a per-channel difference in the mask
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, Hf), torch.linspace(-1, 1, Wf), indexing="ij")
+    coord = torch.stack([xs, ys], -1)[None].repeat(B, 1, 1, 1) * 1.15 + 0.05 * torch.randn(B, Hf, Wf, 2, generator=g)
+    d = lambda t: t.to(dev())
+    fused, _ = S.post_fusion_compose(d(lip), d(face), d(gt), d(mask), d(coord), x0, y0, paste_shift=True,
+                                     expand_pad=lw // 5 if expand else -1, want_canonical=False)
+    want, _ = O.post_fusion_compose(lip, face, gt, mask, x0, y0, coord, expand_lip_mask=expand)
+    got = fused.permute(0, 2, 3, 1).cpu()
+    inside = (got != gt).any(-1).float().mean().item()
+    assert 0.02 < inside < 0.9, inside                                     # both branches of the kernel are exercised
+    assert maxabs(got, want) < 2e-6
+
+
 def test_talking_face_post_fusion_uses_kernel(S, golden):
     cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
     m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval").to(dev()).eval()

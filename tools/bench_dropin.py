@@ -38,3 +38,21 @@ for prec in ("bf16x3", "fp16f8"):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print("drop-in loop %dx%d %s: %.0f frames/s (%.3f ms/frame), no host sync in the body" % (H, W, prec, 64 / dt, dt / 64 * 1e3))
+
+if "--profile" in sys.argv:
+    # where the per-frame time goes: host enqueue time (loop without the final synchronise) and per-kernel device time
+    tf.dropin_precision = "bf16x3"
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(64):
+        frame(i)
+    t_enq = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    print("host enqueue %.3f ms/frame, with device drain %.3f ms/frame" % (t_enq / 64 * 1e3, t_all / 64 * 1e3))
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for i in range(16):
+            frame(i)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
