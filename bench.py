@@ -868,6 +868,91 @@ def run_config5(a):
     print(json.dumps(line))
 
 
+def run_config5_dp(a, H=80, W=120, frames=4, window=5):
+    """BASELINE.json configs[4] on N GPUs: data-parallel over frames as the reference trains (DistributedSampler, train.py:102;
+    DDP, training.py:40) — every rank renders ITS 4 frames x (1 + 5 sync-window) renders, forward + backward on the tensor-core
+    training kernels, then ONE gradient exchange of the flat hot-path bucket (speech2lip_b200.dist.GradExchange: the library's
+    one-kernel all-reduce over NVLink peer memory) and the SGD step.  Weak scaling (4 frames per GPU).  Reports the step with
+    the peer kernel, the same step with one NCCL all_reduce instead, both exchanges timed alone, and checks that the weights
+    are bit-identical on every rank after the timed steps."""
+    import torch.distributed as dist
+    import speech2lip_b200 as s2l
+    from speech2lip_b200 import synth
+    from speech2lip_b200.dist import GradExchange, broadcast_module
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    G = 1 + window
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_state_dict(rank, "kaiming", 2, 3).items()}   # ranks start DIFFERENT
+    m = s2l.TalkingFace(device=dev, cfg=cfg).to(dev).train()
+    m.load_state_dict(sd, strict=False)
+    broadcast_module(m, src=0)                                            # DDP's constructor broadcast
+    m.invalidate_packed()
+    gen = torch.Generator().manual_seed(100 + rank)                       # every rank its own frames
+    audio = torch.from_numpy(synth.make_audio(frames * G, seed=21 + rank)).to(dev)
+    index = torch.arange(frames * G) + rank * frames * G
+    target = torch.rand(frames * G, H, W, 3, generator=gen).to(dev)
+    hot = [p for n, p in m.named_parameters() if not n.startswith(("post_fusion", "canonical", "coord_"))]
+    opt = torch.optim.SGD(hot, lr=1e-5)
+    exch = {"peer": GradExchange(hot, method="peer"), "nccl": GradExchange(hot, method="collective")}
+
+    def step(method):
+        opt.zero_grad(set_to_none=True)
+        rgb = m.render_lip_train(audio, index, H, W)
+        ((rgb - target) ** 2).mean().backward()
+        exch[method].allreduce()
+        opt.step()
+
+    def timed(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    K, Wm = max(a.steps, 1), max(a.warmup, 3)
+    mon = ClockSampler(local) if rank == 0 else None
+    if mon:
+        mon.start()
+    t_begin = time.perf_counter()
+    ms_peer = timed(lambda: step("peer"), K, Wm)
+    clocks = mon.stop(t_begin, time.perf_counter()) if mon else None
+    ms_nccl = timed(lambda: step("nccl"), K, Wm)
+    for p in hot:                                                         # the exchanges alone, on a populated bucket
+        p.grad = torch.randn_like(p)
+    ex_peer = timed(lambda: exch["peer"].allreduce(), 50, 5)
+    ex_nccl = timed(lambda: exch["nccl"].allreduce(), 50, 5)
+    # after identical averaged gradients the weights must still be bit-identical on every rank
+    digest = torch.stack([p.detach().view(torch.int32).sum(dtype=torch.int64) for p in hot]).sum().reshape(1)
+    alld = [torch.empty_like(digest) for _ in range(world)]
+    dist.all_gather(alld, digest)
+    same = all(bool(torch.equal(d, alld[0])) for d in alld)
+    n_floats = exch["peer"].n
+    exch["peer"].close()
+    if rank == 0:
+        line = {"metric": "training frames/s (4-frame batch per GPU with the 5-frame sync-window renders, lip crop 80x120, fwd+bwd+exchange+SGD)",
+                "value": world * frames / (ms_peer * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_peer, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 (fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4] data-parallel: %d frames x (1 + 5 sync-window) renders x 4 taps per GPU" % frames,
+                           "parallelism": "dp%d over frames; one flat gradient bucket of %d floats (%.2f MB) per step" % (world, n_floats, n_floats * 4 / 1e6)},
+                "exchange": {"kernel": "s2l_allreduce_peer (one launch: signal, wait, sum %d payloads over NVLink peer loads in rank order)" % world,
+                             "ms_peer_kernel": ex_peer, "ms_nccl_all_reduce": ex_nccl, "step_ms_with_peer_kernel": ms_peer,
+                             "step_ms_with_nccl": ms_nccl, "bucket_bytes": n_floats * 4,
+                             "weights_bit_identical_on_all_ranks_after_steps": same},
+                "clocks": clocks}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -875,7 +960,9 @@ def main():
     elif a.config == 3:
         run_config3(a)
     elif a.config == 5:
-        if int(os.environ.get("RANK", "0")) == 0:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            run_config5_dp(a)
+        elif int(os.environ.get("RANK", "0")) == 0:
             run_config5(a)
     else:
         run_gpu_arm(a)

@@ -233,6 +233,23 @@ int32_t s2l_train_rows_fwd(const void* blob, const float* x, int64_t n_rows, con
 int32_t s2l_train_rows_bwd(const void* blob, const float* d_out, const float* x, int64_t n_rows, const int64_t* time_idx_dev,
                            const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream);
 
+/* Data-parallel training exchange (replaces DistributedDataParallel's gradient all-reduce, training.py:40 / train.py:102;
+ * SURVEY 8(e) "Training (C5)").  Each rank allocates ONE buffer (s2l_peer_alloc: flags + two payload buffers of n_floats),
+ * sends its 64-byte CUDA-IPC handle to its peers (any transport — the Python host uses torch.distributed), opens theirs
+ * (s2l_peer_open), and per step: writes its flat gradient bucket at s2l_peer_payload_offset(n_floats, epoch) of its own
+ * buffer (stream order), then calls s2l_allreduce_peer with epoch = 1, 2, 3, ... : ONE kernel that signals, waits for the
+ * peers' signals and sums all payloads over NVLink peer loads in rank order into out (x scale) — bit-identical on every
+ * rank.  peer_bufs is a HOST array of `world` device pointers (this rank's own buffer at index rank).  Every rank must call
+ * with the same epoch sequence; a peer that never arrives traps the kernel after a few seconds instead of hanging. */
+size_t  s2l_peer_buffer_bytes(int64_t n_floats);
+size_t  s2l_peer_payload_offset(int64_t n_floats, uint32_t epoch);
+int32_t s2l_peer_alloc(int64_t n_floats, void** dptr, uint8_t* handle64);
+int32_t s2l_peer_open(const uint8_t* handle64, void** dptr);
+int32_t s2l_peer_close(void* dptr);
+int32_t s2l_peer_free(void* dptr);
+int32_t s2l_allreduce_peer(const void* const* peer_bufs, int32_t rank, int32_t world, int64_t n_floats, float scale, uint32_t epoch,
+                           float* out, void* stream);
+
 /* The GEMMs of the exact fp32 per-call backward (autograd through tf_nerf.py:252-283, loss.backward() training.py:559):
  *   s2l_wgrad_rows_fp32: out[l] [A,B] = dy[l]^T h[l] for n_mats matrices, dy[l] [N,A] / h[l] [N,B] row-major, matrix l at
  *                        dy + l*mat_stride_dy / h + l*mat_stride_h (a stride of 0 shares one operand between the matrices);

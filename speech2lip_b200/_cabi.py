@@ -72,6 +72,13 @@ SYMBOLS = {
     "s2l_train_rows_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "s2l_train_rows_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "s2l_peer_buffer_bytes": (C.c_size_t, [C.c_int64]),
+    "s2l_peer_payload_offset": (C.c_size_t, [C.c_int64, C.c_uint32]),
+    "s2l_peer_alloc": (C.c_int32, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "s2l_peer_open": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "s2l_peer_close": (C.c_int32, [C.c_void_p]),
+    "s2l_peer_free": (C.c_int32, [C.c_void_p]),
+    "s2l_allreduce_peer": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]),
     "s2l_wgrad_rows_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "s2l_wgrad_rows_fp32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["s2l_capi.cu", "s2l_pack.cu", "s2l_audio.cu", "s2l_mlp_fp32.cu", "s2l_mlp_tc.cu", "s2l_mlp_tc2.cu", "s2l_reduce.cu",
-           "s2l_postfusion.cu", "s2l_mlp_bwd.cu", "s2l_train_dgrad.cu", "s2l_train_wgrad.cu", "s2l_train_final.cu", "s2l_gemm_fp32.cu"]
+           "s2l_postfusion.cu", "s2l_mlp_bwd.cu", "s2l_train_dgrad.cu", "s2l_train_wgrad.cu", "s2l_train_final.cu", "s2l_gemm_fp32.cu", "s2l_peer.cu"]
 LIB = os.path.join(HERE, "libs2l_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: frames are independent, so the path shards with no data-path collective
 (SURVEY §8(e)).  One process per GPU; the only communication is ONE broadcast of the hot-path
 parameters from rank 0 at start-up (replaces DistributedDataParallel's constructor broadcast,
-src/face_simple/training.py:40), packed into a single flat buffer so it is one NCCL call."""
+src/face_simple/training.py:40), packed into a single flat buffer so it is one NCCL call.
+Training is data-parallel over frames; its one exchange step — the gradient average — is GradExchange below."""
 import torch
 import torch.distributed as dist
 
@@ -61,3 +62,118 @@ def gather_frames(local_rgb, n_frames, group=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat(outs, 0)[:n_frames]
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Data-parallel TRAINING (BASELINE configs[4]): DP over frames as the reference does it (DistributedSampler,
+# train.py:102; DDP, training.py:40) — every rank renders its own frames, the gradients of one flat bucket are averaged.
+
+
+class _DeviceSpan:
+    """A [n] float32 window of device memory the library allocated, wrapped zero-copy by torch.as_tensor."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class GradExchange:
+    """Averages (or sums) the gradients of `params` over the ranks of `group` as ONE flat bucket per step.
+
+    method="peer" (CUDA): the library's one-kernel all-reduce over NVLink peer memory (s2l_allreduce_peer): every rank's
+        bucket lives in a CUDA-IPC buffer its peers have mapped; the kernel signals, waits and sums all payloads in rank order
+        — bit-identical results on every rank, one launch per step, no NCCL on the path.  The 64-byte IPC handles travel
+        through `group` once, at construction (any backend).  Raises if the handles cannot be exchanged or opened.
+    method="collective": one torch.distributed.all_reduce of the flat bucket (NCCL for CUDA tensors, gloo for CPU tensors) —
+        the library baseline the peer kernel is measured against, and the host-logic path the CPU tests cover."""
+
+    def __init__(self, params, group=None, method="peer", average=True):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("GradExchange: no parameters")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.average = average
+        self.method = method
+        self.n = sum(p.numel() for p in self.params)
+        self.device = self.params[0].device
+        self.epoch = 0
+        if method == "collective":
+            self.flat = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            self._views_out = self._views(self.flat)
+            return
+        if method != "peer":
+            raise ValueError("GradExchange: method must be 'peer' or 'collective'")
+        if self.device.type != "cuda":
+            raise RuntimeError("GradExchange(method='peer') needs CUDA parameters; use method='collective' for CPU tensors")
+        import ctypes as C
+        from . import _cabi
+        self._C, self._cabi, self._lib = C, _cabi, _cabi.lib()
+        with torch.cuda.device(self.device):
+            own, handle = C.c_void_p(), (C.c_uint8 * 64)()
+            _cabi.check(self._lib.s2l_peer_alloc(self.n, C.byref(own), handle), "s2l_peer_alloc")
+            self._own = own.value
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            self._ptrs = (C.c_void_p * self.world)()
+            self._opened = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self._ptrs[r] = self._own
+                    continue
+                p, h = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                _cabi.check(self._lib.s2l_peer_open(h, C.byref(p)), "s2l_peer_open (rank %d)" % r)
+                self._ptrs[r] = p.value
+                self._opened.append(p.value)
+            self._payload = [torch.as_tensor(_DeviceSpan(self._own + self._lib.s2l_peer_payload_offset(self.n, e), self.n),
+                                             device=self.device) for e in (0, 1)]
+            self._views_in = [self._views(t) for t in self._payload]
+            self.flat = torch.empty(self.n, dtype=torch.float32, device=self.device)
+            self._views_out = self._views(self.flat)
+        dist.barrier(group=group)          # every rank has mapped every buffer before the first signal is written
+
+    def _views(self, flat):
+        out, off = [], 0
+        for p in self.params:
+            out.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        return out
+
+    def _fill(self, views):
+        grads = [p.grad if p.grad is not None else None for p in self.params]
+        have = [(v, g) for v, g in zip(views, grads) if g is not None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g.detach() for _, g in have])
+        for v, g in zip(views, grads):
+            if g is None:
+                v.zero_()
+
+    def allreduce(self):
+        """grads of `params` <- mean (or sum) over ranks; afterwards every p.grad is a view into self.flat."""
+        self.epoch += 1
+        scale = 1.0 / self.world if self.average else 1.0
+        with torch.no_grad():
+            if self.method == "collective":
+                self._fill(self._views_out)
+                dist.all_reduce(self.flat, group=self.group)
+                if scale != 1.0:
+                    self.flat.mul_(scale)
+            else:
+                self._fill(self._views_in[self.epoch & 1])
+                with torch.cuda.device(self.device):
+                    self._cabi.check(self._lib.s2l_allreduce_peer(self._ptrs, self.rank, self.world, self.n, scale, self.epoch,
+                                                                  self.flat.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                                     "s2l_allreduce_peer")
+            for p, v in zip(self.params, self._views_out):
+                p.grad = v
+        return self.flat
+
+    def close(self):
+        if self.method == "peer" and getattr(self, "_own", None):
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # nobody is still reading a buffer that is about to be unmapped
+            for p in self._opened:
+                self._lib.s2l_peer_close(p)
+            self._payload = self._views_in = None
+            self._lib.s2l_peer_free(self._own)
+            self._own, self._opened = None, []

@@ -49,7 +49,25 @@ def _worker(rank, world, port, q):
     dist.all_gather(both, digest)
     same_module = bool(torch.equal(both[0], both[1])) and float(m.post_fusion_unet.inc.double_conv[1].running_mean[0]) == 0.5 \
         and int(m.post_fusion_unet.inc.double_conv[1].num_batches_tracked) == 7
-    q.put((rank, same and same_module, ok_gather, (lo, hi)))
+    # data-parallel training exchange, host logic (the flat-bucket path; the one-kernel peer path is a GPU test):
+    # rank-specific gradients, one parameter without a gradient on rank 1, two consecutive steps
+    from speech2lip_b200.dist import GradExchange
+    ps = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    ex = GradExchange(ps, method="collective", average=True)
+    ok_ex = True
+    for step in (1, 2):
+        for i, p in enumerate(ps):
+            p.grad = None if (rank == 1 and i == 1) else torch.full_like(p, float((rank + 1) * (i + 1) * step))
+        ex.allreduce()
+        for i, p in enumerate(ps):
+            want = ((1 + (0 if i == 1 else 2)) * (i + 1) * step) / 2.0
+            ok_ex = ok_ex and bool((p.grad == want).all()) and p.grad.shape == p.shape
+    try:
+        GradExchange(ps, method="peer")
+        ok_ex = False                                 # CPU tensors must be refused loudly, not silently routed elsewhere
+    except RuntimeError:
+        pass
+    q.put((rank, same and same_module and ok_ex, ok_gather, (lo, hi)))
     dist.destroy_process_group()
 
 
