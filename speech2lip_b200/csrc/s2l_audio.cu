@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(256, 1) audio_encode_kernel(const uint8_t* __r
   __shared__ float x1[32 * 8], x2[32 * 4], x3[64 * 2], x4[64], x5[64], lat[64];
   __shared__ float pe[kTimePE];
   __shared__ float b0s[256], bss[256];
+  __shared__ double part0[8][256], part5[8][256];        // folded-bias partial sums: 8 k-slices x this CTA's columns
+  const int nsplit = gridDim.y, sp = blockIdx.y, CW = 256 / nsplit;   // the folded biases' columns are split over gridDim.y CTAs
   extern __shared__ __align__(16) float Ws[];           // AudioNet weights, padded rows (S_* offsets)
   const int tid = threadIdx.x;
   if (gate_flag && *gate_flag == 0) {
@@ -99,9 +101,14 @@ __global__ void __launch_bounds__(256, 1) audio_encode_kernel(const uint8_t* __r
     const char* p0 = reinterpret_cast<const char*>(C + C_FCA_WT);
     const char* p1 = reinterpret_cast<const char*>(C + C_FCAS_WT);
     for (int i = tid; i < 64 * 256 * 4 / 128; i += 256) { prefetch_l2(p0 + i * 128); prefetch_l2(p1 + i * 128); }
-    const char* q0 = reinterpret_cast<const char*>(Fp + f_pts_off(0));
-    const char* q5 = reinterpret_cast<const char*>(Fp + f_pts_off(5));
-    for (int i = tid; i < 256 * 256 * 4 / 128; i += 256) { prefetch_l2(q0 + i * 128); prefetch_l2(q5 + i * 128); }
+    const float* q0 = Fp + f_pts_off(0);
+    const float* q5 = Fp + f_pts_off(5);
+    const int lpr = CW / 32;                               // 128-byte lines of this CTA's columns per weight row
+    for (int i = tid; i < 256 * lpr; i += 256) {
+      const int o = (i / lpr) * 256 + sp * CW + (i % lpr) * 32;
+      prefetch_l2(q0 + o);
+      prefetch_l2(q5 + o);
+    }
   }
   if (!latent_in) {
     stage_layer<32, 29 * 3, kWs0>(Ws + S_CONV0_W, Ws + S_CONV0_B, A + A_CONV0_W, A + A_CONV0_B, tid);
@@ -211,36 +218,48 @@ __global__ void __launch_bounds__(256, 1) audio_encode_kernel(const uint8_t* __r
     }
     b0s[n] = b0;
     bss[n] = bs;
-    float* fb = frame_bias + (size_t)f * 4 * 256;
-    fb[n] = b0;
-    fb[256 + n] = bs;
+    if (sp == 0) {
+      float* fb = frame_bias + (size_t)f * 4 * 256;
+      fb[n] = b0;
+      fb[256 + n] = bs;
+    }
   }
   __syncthreads();
   {
-    // folded biases for the tensor-core path: W0*bias0 + b0 and W5[:, :256]*bias_skip + b5 (fp64 accumulate)
-    const int n = tid;
+    // folded biases for the tensor-core path: W0*bias0 + b0 and W5[:, :256]*bias_skip + b5 (fp64 accumulate).
+    // Work item = (column, k-slice of 32): 8 slices per column, combined in slice order — the same order whether one CTA
+    // owns all 256 columns or gridDim.y CTAs own 256/gridDim.y each (a single frame's constants were one SM pulling 512 KB
+    // of usually-cold weights: 20 us; split 8 ways every load of a CTA is in flight at once).
     const float* W0T = Fp + f_pts_off(0);
     const float* W5T = Fp + f_pts_off(5);
-    // (the blob is often cold here — a drop-in caller's 121 MB tiled window evicts it from L2 between frames — so the 2 x 256
-    //  loads are issued 64 deep per matrix instead of one dependent pair per iteration; the summation order is unchanged)
-    double a0 = 0.0, a5 = 0.0;
-    for (int k0 = 0; k0 < 256; k0 += 64) {
-      float w0[64], w5[64];
+    for (int item = tid; item < CW * 8; item += 256) {
+      const int c = item % CW, ks = item / CW, n = sp * CW + c;
+      float w0[32], w5[32];
 #pragma unroll
-      for (int u = 0; u < 64; ++u) {
-        w0[u] = __ldg(W0T + (k0 + u) * 256 + n);
-        w5[u] = __ldg(W5T + (k0 + u) * 256 + n);
+      for (int u = 0; u < 32; ++u) {
+        w0[u] = __ldg(W0T + (ks * 32 + u) * 256 + n);
+        w5[u] = __ldg(W5T + (ks * 32 + u) * 256 + n);
       }
       asm volatile("" ::: "memory");     // keep the whole batch of loads ahead of the first use
+      double a0 = 0.0, a5 = 0.0;
 #pragma unroll
-      for (int u = 0; u < 64; ++u) {
-        a0 += (double)w0[u] * (double)b0s[k0 + u];
-        a5 += (double)w5[u] * (double)bss[k0 + u];
+      for (int u = 0; u < 32; ++u) {
+        a0 += (double)w0[u] * (double)b0s[ks * 32 + u];
+        a5 += (double)w5[u] * (double)bss[ks * 32 + u];
       }
+      part0[ks][c] = a0;
+      part5[ks][c] = a5;
     }
-    float* fb = frame_bias + (size_t)f * 4 * 256;
-    fb[512 + n] = (float)(a0 + (double)Fp[F_PTS_B + 0 * 256 + n]);
-    fb[768 + n] = (float)(a5 + (double)Fp[F_PTS_B + 5 * 256 + n]);
+    __syncthreads();
+    if (tid < CW) {
+      const int n = sp * CW + tid;
+      double a0 = 0.0, a5 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) { a0 += part0[ks][tid]; a5 += part5[ks][tid]; }
+      float* fb = frame_bias + (size_t)f * 4 * 256;
+      fb[512 + n] = (float)(a0 + (double)Fp[F_PTS_B + 0 * 256 + n]);
+      fb[768 + n] = (float)(a5 + (double)Fp[F_PTS_B + 5 * 256 + n]);
+    }
   }
   }   // frames
 }
@@ -274,7 +293,9 @@ extern "C" int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, in
   if (!blob || !latent || !frame_bias) { set_error("s2l_latent_bias_fwd: null blob/latent/frame_bias"); return 1; }
   if (n_frames < 0 || latent_stride < 0) { set_error("s2l_latent_bias_fwd: negative n_frames/stride"); return 2; }
   if (n_frames == 0) return 0;
-  audio_encode_kernel<<<n_frames, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  // few frames (the drop-in: ONE): split the folded biases' columns over up to 8 CTAs per frame
+  const int nsplit = n_frames <= 18 ? 8 : n_frames <= 37 ? 4 : n_frames <= 74 ? 2 : 1;
+  audio_encode_kernel<<<dim3(n_frames, nsplit), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(blob), blob_layout(), nullptr, 0, reinterpret_cast<const long long*>(frame_idx), nullptr,
       frame_bias, latent, (long long)latent_stride, n_frames, nullptr, nullptr);
   return check_launch("audio_encode_kernel(latent)") ? 0 : 5;
@@ -284,7 +305,7 @@ namespace s2l {
 // flag[0] = 1 when any row differs (bitwise) from row 0 in columns [col0, col0 + ncols); the caller zeroes flag first.
 // One warp per row (grid-stride over rows), lanes stride over the row in 8-byte words when the geometry allows it
 // (row stride, col0 and ncols even, base 8-byte aligned: the drop-in's [N,66] rows and [B,464] windows both qualify).
-template <typename V>
+template <typename V, int NQ>
 __global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __restrict__ x, long long n_rows, long long row_stride,
                                                           int col0, int ncols, int* __restrict__ flag) {
   constexpr int VW = sizeof(V) / 4;
@@ -302,23 +323,24 @@ __global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __rest
     for (int t = 0; t < VW; ++t) d |= pa[t] != pb[t];
     return d;
   };
-  if (nv <= 128) {
-    // a lane owns up to 4 words of the row: row 0's copies stay in registers and two rows (8 loads per lane) are in flight at
-    // once — the 121 MB tiled window of the drop-in caller streams at HBM rate instead of one dependent load per lane
-    V ref[4], a[4], b[4];
+  if (nv <= 32 * NQ) {
+    // a lane owns up to NQ words of a row: row 0's copies stay in registers and RPI rows (16 loads per lane) are in flight
+    // at once — the 121 MB tiled window of the drop-in caller streams at HBM rate instead of one dependent load per lane
+    constexpr int RPI = 16 / NQ;
+    V ref[NQ], a[RPI][NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) ref[q] = (lane + 32 * q < nv) ? __ldg(r0 + lane + 32 * q) : V{};
-    for (long long r = 2 * warp + 1; r < n_rows; r += 2 * n_warps) {
-      const V* ra = reinterpret_cast<const V*>(x + r * row_stride + col0);
-      const V* rb = reinterpret_cast<const V*>(x + (r + 1) * row_stride + col0);
-      const bool two = r + 1 < n_rows;
+    for (int q = 0; q < NQ; ++q) ref[q] = (lane + 32 * q < nv) ? __ldg(r0 + lane + 32 * q) : V{};
+    for (long long r = RPI * warp + 1; r < n_rows; r += RPI * n_warps) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a[q] = (lane + 32 * q < nv) ? ra[lane + 32 * q] : ref[q];
-        b[q] = (two && lane + 32 * q < nv) ? rb[lane + 32 * q] : ref[q];
+      for (int i = 0; i < RPI; ++i) {
+        const V* rr = reinterpret_cast<const V*>(x + (r + i) * row_stride + col0);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) a[i][q] = (r + i < n_rows && lane + 32 * q < nv) ? rr[lane + 32 * q] : ref[q];
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) diff |= ne(a[q], ref[q]) | ne(b[q], ref[q]);
+      for (int i = 0; i < RPI; ++i)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) diff |= ne(a[i][q], ref[q]);
     }
   } else {
     for (long long r = warp + 1; r < n_rows; r += n_warps) {
@@ -337,13 +359,19 @@ extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_s
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
   if (n_rows <= 1 || ncols == 0) return 0;
-  const long long want = (n_rows + 15) / 16;                                 // 8 warps per block, two rows per warp per pass
-  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
   const bool wide = (row_stride % 2 == 0) && (col0 % 2 == 0) && (ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const bool wide4 = (row_stride % 4 == 0) && (col0 % 4 == 0) && (ncols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  if (wide4) rows_differ_kernel<uint4><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
-  else if (wide) rows_differ_kernel<uint2><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
-  else rows_differ_kernel<uint32_t><<<grid > 0 ? grid : 1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n_rows, row_stride, col0, ncols, flag);
+  const int nv = ncols / (wide4 ? 4 : wide ? 2 : 1);
+  const int nq = nv <= 32 ? 1 : nv <= 64 ? 2 : 4;                            // words of a row per lane (register-resident path)
+  const long long rows_per_block = 8 * (16 / nq);                           // 8 warps per block, 16/nq rows per warp per pass
+  const long long want = (n_rows + rows_per_block - 1) / rows_per_block;
+  const int grid = (int)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+#define S2L_RD(V, NQ) rows_differ_kernel<V, NQ><<<grid, 256, 0, st>>>(xw, n_rows, row_stride, col0, ncols, flag)
+  if (wide4) { if (nq == 1) S2L_RD(uint4, 1); else if (nq == 2) S2L_RD(uint4, 2); else S2L_RD(uint4, 4); }
+  else if (wide) { if (nq == 1) S2L_RD(uint2, 1); else if (nq == 2) S2L_RD(uint2, 2); else S2L_RD(uint2, 4); }
+  else { if (nq == 1) S2L_RD(uint32_t, 1); else if (nq == 2) S2L_RD(uint32_t, 2); else S2L_RD(uint32_t, 4); }
+#undef S2L_RD
   return check_launch("rows_differ_kernel") ? 0 : 5;
 }
 
