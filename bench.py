@@ -556,6 +556,15 @@ def run_gpu_arm(a):
                 ms = quick(lambda: r_alt.render_frames(audio_d, index_d, H, W, mode=a.mode, eps_shift=0.001, out=rgb_d))
             extras["same_workload_" + alt] = {"frames_per_s": F / (ms * 1e-3), "ms_per_step": ms,
                                              "parity_mode": alt != "bf16x1"}
+        if vol:
+            # the exact fp32 kernel (CUDA-core FFMA, the arithmetic every parity number is measured against) on ONE frame of
+            # the same workload: frames/s and its fraction of the fp32 FFMA peak (148 SMs x 128 lanes x 2 x SM clock)
+            r32 = s2l.LipRenderer(w, "fp32")
+            ms = quick(lambda: r32.render_frames(audio_d[:1], index_d[:1], H, W, mode="volumetric", rays_o=ro_d, rays_d=rd_d, z_vals=z_d,
+                                                 out=rgb_d[:1]), steps=2)
+            tf = points_per_frame(a) * FLOP_PER_POINT["volumetric"] / (ms * 1e-3) / 1e12
+            extras["same_workload_fp32_exact"] = {"frames_per_s": 1.0 / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": 1,
+                                                  "tflops_algorithmic": tf, "frac_of_fp32_ffma_peak_at_1965mhz": tf / (148 * 128 * 2 * 1.965e9 / 1e12)}
         if vol and a.samples % 16 == 0:
             # Early ray termination (the only results-preserving lever toward the 500 frames/s target — at 64 samples
             # per ray 500 frames/s is 2.6 PFLOP/s of algorithmic work, above the chip's measured dense bf16 peak even at ONE MMA
