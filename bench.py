@@ -479,7 +479,9 @@ def run_gpu_arm(a):
                                           p(rd_d) if vol else None, p(z_d), p(rgb_d), None, None, p(scratch_d), prec, st()), "render")
 
     def step_e2e():
-        """public API on HOST buffers: H2D (windows, indices, pose) -> render -> D2H (frames), all on the current stream"""
+        """public API on HOST buffers: H2D (windows, indices, pose) -> render -> D2H (frames), all on the current stream.
+        (Splitting the step into chunks whose D2H overlaps the next chunk's render — LipRenderer.render_sequence_host — was
+        measured here: 49.5 ms against 49.0 ms, the per-launch fixed work of four 2-frame launches costs more than the 6 MB copy.)"""
         ad = audio_h.to(dev, non_blocking=True)
         idd = index_h.to(dev, non_blocking=True)
         if vol:
