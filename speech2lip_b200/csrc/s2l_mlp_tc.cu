@@ -425,6 +425,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               __nv_bfloat16* dst = a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32;
               st_global_v8(dst, o);
               st_global_v8(dst + 16, o + 8);
+              // the ReLU mask of the same 32 values as one word: the data-gradient kernel reads 4 B instead of these 64 B
+              uint32_t m = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                m |= ((o[j] & 0x00007FFFu) ? (1u << (2 * j)) : 0u) | ((o[j] & 0x7FFF0000u) ? (2u << (2 * j)) : 0u);
+              a.save_mask[(((size_t)g * n_tiles + tile) * 8 + (q * 2 + half)) * TC_TM + row] = m;
             }
 #endif
             tmem_st_wait();
@@ -607,7 +613,7 @@ int launch_mlp_tc(const void* blob, const PointSrc& src, int n_frames, const flo
 // Training forward (s2l_train_fwd): the live 4-tap render of F frames in bf16 with the fused blend epilogue, saving the
 // activations the backward needs.  Always the single-CTA schedule (training launches are a few thousand tiles).
 int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* rgb,
-                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st, float* raw_out) {
+                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, uint32_t* save_mask, cudaStream_t st, float* raw_out) {
   TcArgs a{};
   a.blob = reinterpret_cast<const uint8_t*>(blob);
   a.L = blob_layout();
@@ -621,6 +627,7 @@ int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, con
   a.out = raw_out;
   a.save_h = save_h;
   a.save_pe = save_pe;
+  a.save_mask = save_mask;
   const long long n_tiles = a.tiles_per_frame * n_frames;
   a.rows_total = n_tiles * TC_TM;
   if (n_tiles == 0) return 0;

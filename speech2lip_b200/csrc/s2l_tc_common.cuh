@@ -49,6 +49,7 @@ struct TcArgs {
   //      rows of a tile past the frame's last point hold finite garbage that the backward multiplies by zero gradients)
   __nv_bfloat16* save_h;     // [8][rows_total][256] post-ReLU activations h0..h7 exactly as the next layer's MMA consumed them
   __nv_bfloat16* save_pe;    // [rows_total][64] positional encodings (bf16), the B operand of the fold weight gradients
+  uint32_t* save_mask;       // [8][tiles][8][128] ReLU masks: bit c of word (layer, tile, slice s, row r) = h[row][32 s + c] > 0
   long long rows_total;      // n_tiles * 128
   Gate gate;                 // optional device-side launch gate (s2l_points.cuh)
 };

@@ -26,6 +26,7 @@ namespace s2l {
 struct TrainBufs {
   __nv_bfloat16* h;        // [8][rows_total][256]   saved activations h0..h7 (forward)
   __nv_bfloat16* pe;       // [rows_total][64]       positional encodings (forward)
+  const uint32_t* mask;    // [8][tiles][8][128]     ReLU masks of h0..h7, one word per (row, 32-column slice) (forward)
   __nv_bfloat16* dpre;     // [8][rows_total][256]   dPre0..dPre7 (dgrad)
   __nv_bfloat16* dout16;   // [rows_total][16]       dOut padded to 16 channels (dgrad prologue)
   float* partials;         // wgrad slab partials (WgPlan::total_floats)

@@ -45,13 +45,13 @@ struct DgArgs {
   TrainBufs B;
 };
 
-// fp32 accumulator slice (32 columns) + the matching 32 saved activations (16 packed bf16 pairs) -> 16 packed bf16 pairs of
+// fp32 accumulator slice (32 columns) + the ReLU mask word of the matching 32 saved activations -> 16 packed bf16 pairs of
 // dPre = dH * [h > 0]
-__device__ __forceinline__ void mask_slice(const uint32_t (&v)[32], const uint32_t (&hw)[16], uint32_t (&o)[16]) {
+__device__ __forceinline__ void mask_slice(const uint32_t (&v)[32], uint32_t m, uint32_t (&o)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const float x0 = (hw[j] & 0x00007FFFu) ? __uint_as_float(v[2 * j]) : 0.f;
-    const float x1 = (hw[j] & 0x7FFF0000u) ? __uint_as_float(v[2 * j + 1]) : 0.f;
+    const float x0 = (m & (1u << (2 * j))) ? __uint_as_float(v[2 * j]) : 0.f;
+    const float x1 = (m & (2u << (2 * j))) ? __uint_as_float(v[2 * j + 1]) : 0.f;
     o[j] = cvt_bf16x2(x0, x1);
   }
 }
@@ -255,17 +255,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
       for (int step = 0; step < 8; ++step) {          // step s produces dPre_{7-s} from the accumulator of T8 / layer l = 8-s
         const int hl = 7 - step;
         const uint32_t d_region = tmem_base + (rp ? 256u : 0u);
-        const __nv_bfloat16* hrow = a.B.h + ((size_t)hl * RT + grow) * 256;
+        const uint32_t* mrow = a.B.mask + (((size_t)hl * n_tiles + tile) * 8) * TC_TM + row;
         __nv_bfloat16* drow = a.B.dpre + ((size_t)hl * RT + grow) * 256;
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
-          uint32_t hm[2][16];
+          uint32_t hm[2];
 #pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            const __nv_bfloat16* src = hrow + hh * 128 + qq * 64 + half * 32;
-            ld_global_nc_v8(src, hm[qq]);
-            ld_global_nc_v8(src + 16, hm[qq] + 8);
-          }
+          for (int qq = 0; qq < 2; ++qq) hm[qq] = __ldg(mrow + (hh * 4 + qq * 2 + half) * TC_TM);
           if (step == 0) {
             mbar_wait_wd(&acc_t8[hh], (uint32_t)(it & 1), 710 + hh);
           } else {

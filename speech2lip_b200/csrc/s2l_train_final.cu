@@ -8,7 +8,7 @@
 namespace s2l {
 
 int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, const float* frame_bias, float* rgb,
-                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, cudaStream_t st, float* raw_out = nullptr);
+                        __nv_bfloat16* save_h, __nv_bfloat16* save_pe, uint32_t* save_mask, cudaStream_t st, float* raw_out = nullptr);
 int launch_dgrad_tc(const void* blob, const PointSrc& src, int n_frames, const float* d_rgb, const TrainBufs& B, cudaStream_t st,
                     const float* d_out_rows = nullptr);
 int launch_wgrad_tc(const WgPlan& plan, const TrainBufs& B, cudaStream_t st);
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) wg_frame_terms_kernel(const uint8_t* __re
 
 struct TrainLayout {
   long long rows_total;
-  size_t off_h, off_pe, off_dpre, off_dout, off_part, off_red, off_dbout, total;
+  size_t off_h, off_pe, off_dpre, off_dout, off_part, off_red, off_dbout, off_mask, total;
 };
 static TrainLayout train_layout_pts(long long P, int n_frames, int sms) {
   TrainLayout t{};
@@ -204,6 +204,7 @@ static TrainLayout train_layout_pts(long long P, int n_frames, int sms) {
   t.off_part = o; o = al(o + (size_t)pl.total_floats() * 4);
   t.off_red = o;  o = al(o + (size_t)red_floats(n_frames) * 4);
   t.off_dbout = o; o = al(o + (size_t)kDboutRows * 4 * 4);
+  t.off_mask = o; o = al(o + (size_t)8 * t.rows_total * 8 * 4);      // 8 layers x 8 words per row
   t.total = o;
   return t;
 }
@@ -259,7 +260,8 @@ extern "C" int32_t s2l_train_fwd(const void* blob, const S2LGeom* geom, const fl
   int rc = s2l_latent_bias_fwd(blob, latent, 64, frame_idx, frame_bias, geom->n_frames, stream);
   if (rc) return rc;
   return launch_mlp_tc_train(blob, train_src(*geom), geom->n_frames, frame_bias, rgb, reinterpret_cast<__nv_bfloat16*>(ws + t.off_h),
-                             reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe), reinterpret_cast<cudaStream_t>(stream));
+                             reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe), reinterpret_cast<uint32_t*>(ws + t.off_mask),
+                             reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dgrad -> wgrad -> slab reduction -> fold chain rule -> per-frame terms, shared by the render and the rows entry points
@@ -277,6 +279,7 @@ static int train_backward(const void* blob, const PointSrc& src, int F, const Tr
   TrainBufs B{};
   B.h = reinterpret_cast<__nv_bfloat16*>(ws + t.off_h);
   B.pe = reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe);
+  B.mask = reinterpret_cast<const uint32_t*>(ws + t.off_mask);
   B.dpre = reinterpret_cast<__nv_bfloat16*>(ws + t.off_dpre);
   B.dout16 = reinterpret_cast<__nv_bfloat16*>(ws + t.off_dout);
   B.partials = reinterpret_cast<float*>(ws + t.off_part);
@@ -343,7 +346,8 @@ extern "C" int32_t s2l_train_rows_fwd(const void* blob, const float* x, int64_t 
   int rc = s2l_latent_bias_fwd(blob, x + 2, 2 + kLatent, time_idx_dev, frame_bias, 1, stream);
   if (rc) return rc;
   return launch_mlp_tc_train(blob, rows_src(x, n_rows), 1, frame_bias, nullptr, reinterpret_cast<__nv_bfloat16*>(ws + t.off_h),
-                             reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe), reinterpret_cast<cudaStream_t>(stream), out);
+                             reinterpret_cast<__nv_bfloat16*>(ws + t.off_pe), reinterpret_cast<uint32_t*>(ws + t.off_mask),
+                             reinterpret_cast<cudaStream_t>(stream), out);
 }
 extern "C" int32_t s2l_train_rows_bwd(const void* blob, const float* d_out, const float* x, int64_t n_rows, const int64_t* time_idx_dev,
                                       const float* frame_bias, void* workspace, float* const* grads_host, float* d_latent, void* stream) {
