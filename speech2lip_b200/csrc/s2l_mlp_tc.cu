@@ -423,8 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #ifndef S2L_DBG_NOSAVEH
             if (TRAIN && tile < n_tiles) {     // h_g as the next layer consumes it: 32 bf16 = 64 B of this row
               __nv_bfloat16* dst = a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32;
-              st_global_v8(dst, o);
-              st_global_v8(dst + 16, o + 8);
+              st_rows64_paired(dst, 512, o, lane);
               // the ReLU mask of the same 32 values as one word: the data-gradient kernel reads 4 B instead of these 64 B
               uint32_t m = 0;
 #pragma unroll

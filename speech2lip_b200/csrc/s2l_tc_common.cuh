@@ -175,6 +175,25 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
                "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// Each lane holds 64 B (16 words) of ITS row; rows are row_stride_bytes apart.  A plain pair of 32-byte stores per lane makes
+// every warp instruction 32 separate sectors in 32 lines (ncu: the LSU data pipe of the training kernels was 75 % busy, mostly
+// these).  Lane pairs swap one sector through a shuffle so that each store instruction writes the 64 contiguous bytes of ONE
+// row from two adjacent lanes: half the wavefronts for the same bytes.  All 32 lanes must be active.
+__device__ __forceinline__ void st_rows64_paired(void* my_row, long long row_stride_bytes, const uint32_t* o, int lane) {
+  const bool odd = lane & 1;
+  uint32_t r[8], s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __shfl_xor_sync(0xffffffffu, odd ? o[j] : o[8 + j], 1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s0[j] = odd ? r[j] : o[j];          // row of the even lane: sector 0 from the even lane, sector 1 (received) from the odd one
+    s1[j] = odd ? o[8 + j] : r[j];      // row of the odd lane
+  }
+  char* even_row = reinterpret_cast<char*>(my_row) - (odd ? row_stride_bytes : 0);
+  const int sec = odd ? 32 : 0;
+  st_global_v8(even_row + sec, s0);
+  st_global_v8(even_row + row_stride_bytes + sec, s1);
+}
 __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* r) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])

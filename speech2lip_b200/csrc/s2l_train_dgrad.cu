@@ -279,8 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
             tmem_ld_wait();
             mask_slice(v, hm[qq], o);
             if (step < 7) tmem_st16(taddr, o);          // dPre0 feeds no further layer
-            st_global_v8(drow + q * 64 + half * 32, o);
-            st_global_v8(drow + q * 64 + half * 32 + 16, o + 8);
+            st_rows64_paired(drow + q * 64 + half * 32, 512, o, lane);
             if (step < 7) {
               tmem_st_wait();
               tc_fence_before();
