@@ -640,15 +640,15 @@ def run_gpu_arm(a):
                     ab = tf.audio_merge_forward(au)
                     xx = torch.cat([coords[:, None, :], ab[:, None, :]], -1).view(-1, tf.audio_dims + 2)
                     return tf.rgb_forward(xx, time_pts=torch.tensor([i], device=dev), rgb_pts=None)[:, :3]
-            for i in range(3):
+            for i in range(8):
                 dropin_frame(i)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for i in range(32):
-                dropin_frame(i)
+            for i in range(96):
+                dropin_frame(i % 32)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            extras["drop_in_inference_loop_%dx%d" % (H, W)] = {"frames_per_s": 32 / dt, "ms_per_step": dt / 32 * 1e3, "frames_per_step": 1,
+            extras["drop_in_inference_loop_%dx%d" % (H, W)] = {"frames_per_s": 96 / dt, "ms_per_step": dt / 96 * 1e3, "frames_per_step": 1,
                                                               "precision": tf.dropin_precision,
                                                               "what": "inference.py:144-159 call sequence through TalkingFace, wall clock incl. Python"}
         except Exception as e:      # an extra must never take the headline line down
