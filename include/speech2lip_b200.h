@@ -310,6 +310,15 @@ int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* face_canonica
                                 int32_t lefttop_x, int32_t lefttop_y, int32_t paste_shift, int32_t expand_pad,
                                 float* fused_nchw, float* merged_canonical, void* stream);
 
+/* Backward of s2l_post_fusion_compose w.r.t. the lip crop — the only input that carries a gradient in training
+ * (autograd through tf_nerf.py:334-386 from training.py:436-445, 559).  d_fused_nchw [B,3,out_h,out_w] and/or
+ * d_merged_canonical [B,face_h,face_w,3] may be NULL (no gradient through that output); d_rgb_lip [B,lip_h,lip_w,3] is
+ * overwritten.  The warp term is scattered with fp32 atomics (as ATen's grid_sampler backward does). */
+int32_t s2l_post_fusion_compose_bwd(const float* d_fused_nchw, const float* d_merged_canonical, const float* mask_lip_canonical,
+                                    const float* coord, int32_t batch, int32_t lip_h, int32_t lip_w, int32_t face_h, int32_t face_w,
+                                    int32_t out_h, int32_t out_w, int32_t lefttop_x, int32_t lefttop_y, int32_t paste_shift,
+                                    int32_t expand_pad, float* d_rgb_lip, void* stream);
+
 /* Replaces: the windowing of preprocess/deepspeech_features/deepspeech_features.py:65-75 (zero-pad 8 rows on both
  * sides, 16-row windows, stride 2): logits [T,29] -> windows [ceil(T/2),16,29]  (the hot path's input format). */
 int32_t s2l_audio_windows(const float* logits, int64_t n_steps, float* windows, void* stream);

@@ -94,6 +94,7 @@ SYMBOLS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "s2l_post_fusion_compose": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32] * 11 + [C.c_void_p] * 3),
     "s2l_audio_windows": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "s2l_post_fusion_compose_bwd": (C.c_int32, [C.c_void_p] * 4 + [C.c_int32] * 11 + [C.c_void_p, C.c_void_p]),
     "s2l_frames_to_bgr8": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "s2l_sizeof_geom": (C.c_int32, []),
     "s2l_profile_enable": (None, [C.c_int32]),

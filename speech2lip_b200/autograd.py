@@ -301,3 +301,35 @@ class FusedMLPRowsTC(torch.autograd.Function):
 def rgb_forward_train_tc(module, x, time_pts):
     sd = module._hot_params()
     return FusedMLPRowsTC.apply(x, time_pts, module.packed_weights(), *[sd[n] for n in MLP_PARAM_NAMES])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Post-fusion compose with a gradient to the lip crop (training.py:436-445: the lip render is pasted, warped and refined
+# by the UNet; the loss gradient has to come back to the lip MLP).  Forward = the fused gather-blend kernel, backward =
+# its scatter kernel.  Replaces autograd through F.pad / the mask blend / 2x F.grid_sample of tf_nerf.py:334-386.
+class PostFusionCompose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb_lip, face, gt, mask, coord, x0, y0, paste_shift, expand_pad):
+        from .renderer import post_fusion_compose
+        fused, canon = post_fusion_compose(rgb_lip, face, gt, mask, coord, x0, y0, paste_shift, expand_pad)
+        m = mask.detach().contiguous().float()
+        if m.shape[-1] == 1:
+            m = m.expand(-1, -1, -1, 3).contiguous()
+        ctx.save_for_backward(m, coord.detach().contiguous().float())
+        ctx.geom = (tuple(rgb_lip.shape), tuple(face.shape), int(x0), int(y0), bool(paste_shift), int(expand_pad))
+        ctx.set_materialize_grads(False)          # an output nobody differentiates arrives as None, not as a zero tensor
+        return fused, canon
+
+    @staticmethod
+    def backward(ctx, d_fused, d_canon):
+        lib = _cabi.lib()
+        mask, coord = ctx.saved_tensors
+        (B, lh, lw, _), (_, h, w, _), x0, y0, shift, pad = ctx.geom
+        Hf, Wf = coord.shape[1], coord.shape[2]
+        d_lip = torch.empty(B, lh, lw, 3, device=mask.device)
+        df = d_fused.contiguous().float() if d_fused is not None else None
+        dc = d_canon.contiguous().float() if d_canon is not None else None
+        with torch.cuda.device(mask.device):
+            _cabi.check(lib.s2l_post_fusion_compose_bwd(_ptr(df), _ptr(dc), _ptr(mask), _ptr(coord), B, lh, lw, h, w, Hf, Wf, x0, y0,
+                                                        1 if shift else 0, pad, _ptr(d_lip), _stream()), "s2l_post_fusion_compose_bwd")
+        return d_lip, None, None, None, None, None, None, None, None

@@ -163,6 +163,83 @@ __global__ void __launch_bounds__(256) post_fusion_kernel4(PfArgs a) {
 // gather from there — was built and measured: 0.41 ms vs 0.31 ms for this direct kernel on 64 frames of 500x500; the bounding-box
 // reduction, the fill phase and its barriers cost more than the 4x texel reuse saves while the taps already hit L1.  Removed.)
 
+// ---- backward w.r.t. the lip crop (training: the lip image is the only input that carries a gradient, training.py:436-445):
+//   fused[c]  = [macc_c != 0] * sum_t tw_t * (m_t,c * lip_t,c + (1 - m_t,c) * face_t,c)   ->  d lip_t,c += [macc_c != 0] tw_t m_t,c dF_c
+//   canon[c]  = m * lip_pad + (1 - m) * face                                             ->  d lip    += m dCanon
+// d_lip is first SET by the gather kernel (the canonical term or zero), then the warp term is scattered with atomics (the
+// inverse of the sampling grid is not known; ATen's grid_sampler backward does the same).
+__global__ void pf_bwd_init_kernel(PfArgs a, const float* __restrict__ d_canon, float* __restrict__ d_lip) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)a.B * a.lh * a.lw * 3;
+  if (gid >= n) return;
+  float v = 0.f;
+  if (d_canon) {
+    const int c = (int)(gid % 3);
+    const long long p = gid / 3;
+    const int lx = (int)(p % a.lw), ly = (int)((p / a.lw) % a.lh), b = (int)(p / ((long long)a.lw * a.lh));
+    const size_t idx = (((size_t)b * a.h + (ly + a.py0)) * a.w + (lx + a.px0)) * 3 + c;
+    v = a.mask[idx] * d_canon[idx];
+  }
+  d_lip[gid] = v;
+}
+
+template <bool RECT>
+__global__ void __launch_bounds__(256) pf_bwd_scatter_kernel(PfArgs a, const float* __restrict__ d_fused, float* __restrict__ d_lip) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npix = a.Hf * a.Wf, b = blockIdx.y;
+  if (pix >= npix) return;
+  const float2 g = reinterpret_cast<const float2*>(a.coord)[(size_t)b * npix + pix];
+  const float* __restrict__ mask = a.mask + (size_t)b * a.h * a.w * 3;
+  float* __restrict__ dl = d_lip + (size_t)b * a.lh * a.lw * 3;
+  // the same tap geometry as the forward (pf_pixel_value)
+  const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.x, 1.f), (float)a.w), 1.f), 0.5f);
+  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g.y, 1.f), (float)a.h), 1.f), 0.5f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = __fsub_rn(ix, fx), wy1 = __fsub_rn(iy, fy);
+  const float wx0 = __fsub_rn((float)(x0 + 1), ix), wy0 = __fsub_rn((float)(y0 + 1), iy);
+  const float tw[4] = {__fmul_rn(wx0, wy0), __fmul_rn(wx1, wy0), __fmul_rn(wx0, wy1), __fmul_rn(wx1, wy1)};
+  const int tx[4] = {x0, x0 + 1, x0, x0 + 1}, ty[4] = {y0, y0, y0 + 1, y0 + 1};
+  float mk[4][3], macc[3] = {0.f, 0.f, 0.f};
+  bool tin[4], lin[4], any_lip = false;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    tin[t] = (unsigned)tx[t] < (unsigned)a.w && (unsigned)ty[t] < (unsigned)a.h;
+    lin[t] = tin[t] && (unsigned)(tx[t] - a.px0) < (unsigned)a.lw && (unsigned)(ty[t] - a.py0) < (unsigned)a.lh;
+    any_lip |= lin[t];
+  }
+  if (!any_lip) return;                                    // no tap of this pixel touches the lip crop
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mk[t][c] = tin[t] ? __ldg(mask + (ty[t] * a.w + tx[t]) * 3 + c) : 0.f;
+  if (RECT) {
+    float m = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const bool rin = tx[t] >= a.rx0 && tx[t] < a.rx1 && ty[t] >= a.ry0 && ty[t] < a.ry1;
+      if (tin[t]) m = __fadd_rn(m, __fmul_rn(rin ? 1.f : 0.f, tw[t]));
+    }
+    macc[0] = macc[1] = macc[2] = m;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (tin[t]) macc[c] = __fadd_rn(macc[c], __fmul_rn(mk[t][c], tw[t]));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (macc[c] == 0.f) continue;
+    const float gf = d_fused[((size_t)b * 3 + c) * npix + pix];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float v = tw[t] * mk[t][c] * gf;
+      if (lin[t] && v != 0.f) atomicAdd(dl + ((ty[t] - a.py0) * a.lw + (tx[t] - a.px0)) * 3 + c, v);
+    }
+  }
+}
+
 __global__ void merged_canonical_kernel(PfArgs a, float* __restrict__ out) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)a.B * a.h * a.w * 3;
@@ -177,6 +254,35 @@ __global__ void merged_canonical_kernel(PfArgs a, float* __restrict__ out) {
 
 using namespace s2l;
 
+// shared argument validation / geometry of the forward and backward entry points
+static int32_t pf_setup(PfArgs& a, const char* who, int32_t batch, int32_t lip_h, int32_t lip_w, int32_t face_h, int32_t face_w, int32_t out_h,
+                        int32_t out_w, int32_t lefttop_x, int32_t lefttop_y, int32_t paste_shift, int32_t expand_pad) {
+  if (batch < 0 || lip_h <= 0 || lip_w <= 0 || face_h <= 0 || face_w <= 0 || out_h <= 0 || out_w <= 0) {
+    set_error("%s: bad sizes", who);
+    return 2;
+  }
+  a.B = batch; a.lh = lip_h; a.lw = lip_w; a.h = face_h; a.w = face_w; a.Hf = out_h; a.Wf = out_w;
+  // F.pad(left+1, ..., up+1, ...) with left = x-1, up = y-1 for the 'may'-style datasets, else (left, up)  (tf_nerf.py:345-350)
+  a.px0 = paste_shift ? lefttop_x : lefttop_x - 1;
+  a.py0 = paste_shift ? lefttop_y : lefttop_y - 1;
+  if (a.px0 < 0 || a.py0 < 0 || a.px0 + lip_w > face_w || a.py0 + lip_h > face_h) {
+    set_error("%s: lip crop (%dx%d at %d,%d) does not fit the %dx%d canonical face", who, lip_w, lip_h, a.px0, a.py0, face_w, face_h);
+    return 2;
+  }
+  a.rect = expand_pad >= 0;
+  if (a.rect) {
+    // mask[:, y-p : y+lh+2p, x-p : x+lw+p] = 1                  (tf_nerf.py:362)
+    if (lefttop_y - expand_pad < 0 || lefttop_x - expand_pad < 0) { set_error("%s: expanded mask starts outside the image", who); return 2; }
+    a.ry0 = lefttop_y - expand_pad; a.ry1 = min(face_h, lefttop_y + lip_h + 2 * expand_pad);
+    a.rx0 = lefttop_x - expand_pad; a.rx1 = min(face_w, lefttop_x + lip_w + expand_pad);
+  }
+  if ((long long)face_h * face_w * 3 >= 0x7fffffffll || (long long)out_h * out_w >= 0x7fffffffll || batch > 65535) {
+    set_error("%s: image planes beyond 2^31 elements / batch beyond 65535 are not supported", who);
+    return 2;
+  }
+  return 0;
+}
+
 extern "C" int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* face_canonical, const float* rgb_gt,
                                            const float* mask_lip_canonical, const float* coord, int32_t batch, int32_t lip_h,
                                            int32_t lip_w, int32_t face_h, int32_t face_w, int32_t out_h, int32_t out_w,
@@ -186,33 +292,12 @@ extern "C" int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* fa
     set_error("s2l_post_fusion_compose: null argument");
     return 1;
   }
-  if (batch < 0 || lip_h <= 0 || lip_w <= 0 || face_h <= 0 || face_w <= 0 || out_h <= 0 || out_w <= 0) {
-    set_error("s2l_post_fusion_compose: bad sizes");
-    return 2;
-  }
   PfArgs a{};
   a.lip = rgb_lip; a.face = face_canonical; a.gt = rgb_gt; a.mask = mask_lip_canonical; a.coord = coord; a.fused = fused_nchw;
-  a.B = batch; a.lh = lip_h; a.lw = lip_w; a.h = face_h; a.w = face_w; a.Hf = out_h; a.Wf = out_w;
-  // F.pad(left+1, ..., up+1, ...) with left = x-1, up = y-1 for the 'may'-style datasets, else (left, up)  (tf_nerf.py:345-350)
-  a.px0 = paste_shift ? lefttop_x : lefttop_x - 1;
-  a.py0 = paste_shift ? lefttop_y : lefttop_y - 1;
-  if (a.px0 < 0 || a.py0 < 0 || a.px0 + lip_w > face_w || a.py0 + lip_h > face_h) {
-    set_error("s2l_post_fusion_compose: lip crop (%dx%d at %d,%d) does not fit the %dx%d canonical face", lip_w, lip_h, a.px0, a.py0, face_w, face_h);
-    return 2;
-  }
-  a.rect = expand_pad >= 0;
-  if (a.rect) {
-    // mask[:, y-p : y+lh+2p, x-p : x+lw+p] = 1                  (tf_nerf.py:362)
-    if (lefttop_y - expand_pad < 0 || lefttop_x - expand_pad < 0) { set_error("s2l_post_fusion_compose: expanded mask starts outside the image"); return 2; }
-    a.ry0 = lefttop_y - expand_pad; a.ry1 = min(face_h, lefttop_y + lip_h + 2 * expand_pad);
-    a.rx0 = lefttop_x - expand_pad; a.rx1 = min(face_w, lefttop_x + lip_w + expand_pad);
-  }
+  if (int32_t rc = pf_setup(a, "s2l_post_fusion_compose", batch, lip_h, lip_w, face_h, face_w, out_h, out_w, lefttop_x, lefttop_y, paste_shift,
+                            expand_pad)) return rc;
   if (batch == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if ((long long)face_h * face_w * 3 >= 0x7fffffffll || (long long)out_h * out_w >= 0x7fffffffll || batch > 65535) {
-    set_error("s2l_post_fusion_compose: image planes beyond 2^31 elements / batch beyond 65535 are not supported");
-    return 2;
-  }
   const int npix = out_h * out_w;
   const bool vec4 = (npix % 4 == 0) && ((reinterpret_cast<uintptr_t>(coord) | reinterpret_cast<uintptr_t>(rgb_gt) |
                                          reinterpret_cast<uintptr_t>(fused_nchw)) & 15) == 0;
@@ -230,6 +315,29 @@ extern "C" int32_t s2l_post_fusion_compose(const float* rgb_lip, const float* fa
     const long long m = (long long)batch * face_h * face_w * 3;
     merged_canonical_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a, merged_canonical);
     if (!check_launch("merged_canonical_kernel")) return 5;
+  }
+  return 0;
+}
+
+extern "C" int32_t s2l_post_fusion_compose_bwd(const float* d_fused_nchw, const float* d_merged_canonical, const float* mask_lip_canonical,
+                                               const float* coord, int32_t batch, int32_t lip_h, int32_t lip_w, int32_t face_h,
+                                               int32_t face_w, int32_t out_h, int32_t out_w, int32_t lefttop_x, int32_t lefttop_y,
+                                               int32_t paste_shift, int32_t expand_pad, float* d_rgb_lip, void* stream) {
+  if (!mask_lip_canonical || !coord || !d_rgb_lip) { set_error("s2l_post_fusion_compose_bwd: null argument"); return 1; }
+  PfArgs a{};
+  a.mask = mask_lip_canonical; a.coord = coord;
+  if (int32_t rc = pf_setup(a, "s2l_post_fusion_compose_bwd", batch, lip_h, lip_w, face_h, face_w, out_h, out_w, lefttop_x, lefttop_y,
+                            paste_shift, expand_pad)) return rc;
+  if (batch == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = (long long)batch * lip_h * lip_w * 3;
+  pf_bwd_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, d_merged_canonical, d_rgb_lip);
+  if (!check_launch("pf_bwd_init_kernel")) return 5;
+  if (d_fused_nchw) {
+    const dim3 grid((unsigned)((out_h * out_w + 255) / 256), (unsigned)batch);
+    if (a.rect) pf_bwd_scatter_kernel<true><<<grid, 256, 0, st>>>(a, d_fused_nchw, d_rgb_lip);
+    else pf_bwd_scatter_kernel<false><<<grid, 256, 0, st>>>(a, d_fused_nchw, d_rgb_lip);
+    if (!check_launch("pf_bwd_scatter_kernel")) return 5;
   }
   return 0;
 }

@@ -310,18 +310,26 @@ class TalkingFace(nn.Module):
             return None
         shifted_ds = any(s in self.data_path for s in ('macron', 'obama_adnerf', 'obama2_face_crop', 'may'))
         aug = use_post_fusion_blackaug and random.random() > 0.5        # same RNG draw as tf_nerf.py:369
-        needs_grad = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad
-                                                     for t in (rgb_lip_warped, rgb_face_canonical, rgb_gt, coord))
-        if rgb_lip_warped.is_cuda and not aug and not needs_grad:
-            # fused gather-blend kernel; the UNet stays cuDNN.  The kernel's outputs carry no grad_fn,
-            # so whenever a gradient has to reach the lip MLP (training.py:436-445, 525-539) the differentiable branch
-            # below runs instead.
+        grad_on = torch.is_grad_enabled()
+        lip_grad = grad_on and rgb_lip_warped.requires_grad
+        other_grad = grad_on and any(isinstance(t, torch.Tensor) and t.requires_grad
+                                     for t in (rgb_face_canonical, rgb_gt, coord, mask_lip_canonical))
+        if rgb_lip_warped.is_cuda and not aug and not other_grad:
+            # fused gather-blend kernel; the UNet stays cuDNN.  In training the lip crop is the only
+            # input with a gradient (training.py:436-445, 525-539): the kernel then runs inside an autograd.Function whose
+            # backward is the scatter kernel.  A gradient w.r.t. any other input (or the black-hole augmentation) takes the
+            # differentiable PyTorch branch below.
             lw_ = rgb_lip_warped.shape[2]
             pad_ = -1
             if self.expand_lip_mask:
                 pad_ = lw_ // 12 if 'obama2_face_crop' in self.data_path else lw_ // 5
-            fused, canon = R.post_fusion_compose(rgb_lip_warped, rgb_face_canonical, rgb_gt, mask_lip_canonical, coord,
-                                                 int(lip_lefttop_x), int(lip_lefttop_y), shifted_ds, pad_)
+            if lip_grad:
+                from .autograd import PostFusionCompose
+                fused, canon = PostFusionCompose.apply(rgb_lip_warped, rgb_face_canonical, rgb_gt, mask_lip_canonical, coord,
+                                                       int(lip_lefttop_x), int(lip_lefttop_y), shifted_ds, pad_)
+            else:
+                fused, canon = R.post_fusion_compose(rgb_lip_warped, rgb_face_canonical, rgb_gt, mask_lip_canonical, coord,
+                                                     int(lip_lefttop_x), int(lip_lefttop_y), shifted_ds, pad_)
             recon = self.post_fusion_unet(fused)
             return recon.permute(0, 2, 3, 1), fused.permute(0, 2, 3, 1), canon
         h, w = rgb_face_canonical.shape[1:3]

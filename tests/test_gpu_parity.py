@@ -447,6 +447,49 @@ def test_post_fusion_scalar_and_vector_paths_vs_oracle(S, Hf, Wf, expand):
     assert maxabs(got, want) < 2e-6
 
 
+@pytest.mark.parametrize("expand", [True, False])
+def test_post_fusion_backward_to_the_lip_crop(S, expand):
+    """Training: the lip crop carries the gradient (training.py:436-445).  The drop-in's post_fusion2_onlylip then runs the fused
+    kernel inside an autograd.Function whose backward is the scatter kernel; its gradient must equal autograd through the
+    differentiable PyTorch branch (forced here by asking for a gradient w.r.t. coord as well)."""
+    cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval").to(dev()).eval()
+    m.expand_lip_mask = expand
+    g = torch.Generator().manual_seed(77 + int(expand))
+    B, h, w, lh, lw, x0, y0 = 2, 64, 72, 12, 20, 20, 30
+    lip, face, gt = torch.rand(B, lh, lw, 3, generator=g), torch.rand(B, h, w, 3, generator=g), torch.rand(B, h, w, 3, generator=g)
+    mask = torch.zeros(B, h, w, 3)
+    mask[:, y0 + 1:y0 + lh - 1, x0 + 1:x0 + lw - 1] = 1
+    mask[:, y0 + 3, x0 + 4, 2] = 0.25
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+    coord = torch.stack([xs, ys], -1)[None].repeat(B, 1, 1, 1) * 1.05 + 0.02 * torch.randn(B, h, w, 2, generator=g)
+    r1, r2 = torch.randn(B, h, w, 3, generator=g).to(dev()), torch.randn(B, h, w, 3, generator=g).to(dev())
+    d = lambda t: t.to(dev())
+
+    def run(force_torch, with_unet=False):
+        lp = d(lip).requires_grad_(True)
+        cd = d(coord).requires_grad_(force_torch)
+        from speech2lip_b200 import _cabi
+        _cabi.lib().s2l_launch_count(1)
+        recon, fused, canon = m.post_fusion2_onlylip(lp, d(face), d(gt), d(mask), x0, y0, cd, use_canonical_space=True)
+        n_fwd = int(_cabi.lib().s2l_launch_count(0))     # (the counter is per thread: autograd runs the backward on its own)
+        name = type(canon.grad_fn).__name__
+        # (the UNet term is checked separately and loosely: last-bit differences of its input flip max-pool / ReLU routes)
+        (((recon * r1).sum() if with_unet else 0.0) + (fused * r1).sum() * 0.5 + (canon * r2).sum()).backward()
+        return lp.grad.detach().clone(), fused.detach().clone(), (n_fwd, name)
+    g_k, f_k, n_k = run(False)
+    g_t, f_t, n_t = run(True)
+    assert n_k[0] == 2 and "PostFusionCompose" in n_k[1], n_k        # the fused kernels, inside the autograd.Function
+    assert n_t[0] == 0 and "PostFusionCompose" not in n_t[1], n_t    # the differentiable PyTorch branch
+    assert maxabs(f_k.cpu(), f_t.cpu()) < 2e-6
+    scale = g_t.abs().max().item()
+    err = (g_k - g_t).abs().max().item()
+    print("post-fusion backward (expand=%s): max |d lip| %.3e, max abs difference %.3e" % (expand, scale, err))
+    assert scale > 0 and err <= 2e-5 * scale + 1e-6
+    gu_k, gu_t = run(False, True)[0], run(True, True)[0]
+    assert (gu_k - gu_t).abs().max().item() <= 2e-2 * gu_t.abs().max().item()
+
+
 def test_talking_face_post_fusion_uses_kernel(S, golden):
     cfg = json.load(open(os.path.join(ROOT, "tests", "golden", "may_cfg.json")))
     m = S.TalkingFace(device=dev(), cfg=cfg, mode="eval").to(dev()).eval()
