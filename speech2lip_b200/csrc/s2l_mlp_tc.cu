@@ -420,6 +420,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             else convert_slice<NPASS>(va, b4, o);
             if (NPASS != 1) tmem_st32(taddr, o);
             else tmem_st16(taddr, o);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&epi_done[q]);
+            // (the quarter is released to the MMA thread BEFORE its copy goes to global memory: the stores overlap the next
+            //  layer's first MMAs instead of delaying them)
 #ifndef S2L_DBG_NOSAVEH
             if (TRAIN && tile < n_tiles) {     // h_g as the next layer consumes it: 32 bf16 = 64 B of this row
               __nv_bfloat16* dst = a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32;
@@ -432,9 +437,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               a.save_mask[(((size_t)g * n_tiles + tile) * 8 + (q * 2 + half)) * TC_TM + row] = m;
             }
 #endif
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&epi_done[q]);
             if (tid == 256) TL(1, 9000 + g * 10 + q);      // quarter released to the MMA thread
           }
         }

@@ -278,13 +278,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
             tmem_ld32(taddr, v);
             tmem_ld_wait();
             mask_slice(v, hm[qq], o);
-            if (step < 7) tmem_st16(taddr, o);          // dPre0 feeds no further layer
-            st_rows64_paired(drow + q * 64 + half * 32, 512, o, lane);
-            if (step < 7) {
+            if (step < 7) {                             // dPre0 feeds no further layer
+              tmem_st16(taddr, o);
               tmem_st_wait();
               tc_fence_before();
-              mbar_arrive(&epi_done[q]);
+              mbar_arrive(&epi_done[q]);                // released before the copy to global memory: the stores overlap the next MMAs
             }
+            st_rows64_paired(drow + q * 64 + half * 32, 512, o, lane);
           }
         }
         rp ^= 1;

@@ -214,7 +214,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       float s0 = 0.f, s1 = 0.f;
       for (int c = it.chunk0; c < it.chunk1; ++c) {
         mbar_wait_wd(&full[stage], phase, 300 + stage);
+#ifdef S2L_DBG_WG_NOCOLSUM      // experiment: how much of a chunk's time is the column-sum pass over the staged tile
+        if (false) {
+#else
         if (it.colsum) {
+#endif
           // A tile: block b = channel / 64, row = point: 128 B rows, 16-byte chunks XOR-swizzled with (point & 7)
           const uint8_t* blk = smem + stage * WG_STAGE + (t128 >> 5) * 8192;
           const int cb = (t128 & 31) * 4;                 // byte offset of the channel pair inside the unswizzled row
