@@ -36,9 +36,11 @@
 // Warp roles (512 threads): w0 weight producer (one lane), w1 MMA issuer (whole warp, one elected lane issues),
 // w2 TMEM allocator, w3 idle,
 // w4-7 PE producers, w8-15 epilogue (two warps per TMEM lane quadrant, 32 columns each).
+#include <cuda.h>          // CUtensorMap (type only)
 #include <cstdlib>
 #include <type_traits>
 #include "s2l_tc_common.cuh"
+#include "s2l_train.cuh"
 
 namespace s2l {
 
@@ -61,7 +63,10 @@ static_assert(T1_SMEM_BYTES <= 232448, "shared memory budget");
 // TRAIN (bf16 single pass only): additionally saves h0..h7 and the positional encodings for the backward kernels
 // (s2l_train_dgrad.cu, s2l_train_wgrad.cu).
 template <int NPASS, int UVD, int CL, bool TRAIN = false>
-__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap hmap) {
+  // hmap (TRAIN only): [8 * rows_total][256] bf16 view of save_h, box 32 rows x 32 columns, SWIZZLE_64B — the epilogue warps
+  // stage their slices in the ring stages' unused second planes (a single-pass kernel streams only the first) and the TMA
+  // engine writes them out
   if (a.gate.flag && *a.gate.flag != a.gate.value) return;      // gated launch: the other implementation serves this call
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T1_SM_BAR);
@@ -383,6 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     int rp = 0;
     long long it = 0;
     int fcur = 0;
+    uint32_t n_staged = 0;                                // TRAIN: slices this warp has handed to the TMA engine
+    uint8_t* const stage_slot = smem + SM_STG + kGranPlane + (warp - 8) * 2048;   // + (n_staged & 3) * T1_STAGE
     TL_DECL;
     for (long long tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
@@ -427,8 +434,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             //  layer's first MMAs instead of delaying them)
 #ifndef S2L_DBG_NOSAVEH
             if (TRAIN && tile < n_tiles) {     // h_g as the next layer consumes it: 32 bf16 = 64 B of this row
-              __nv_bfloat16* dst = a.save_h + ((size_t)g * a.rows_total + (size_t)tile * TC_TM + row) * 256 + q * 64 + half * 32;
-              st_rows64_paired(dst, 512, o, lane);
+              uint8_t* slot = stage_slot + (n_staged & 3u) * T1_STAGE;
+              if (lane == 0) bulk_wait_group_read<3>();       // the store that last read this slot (four slices ago) has drained it
+              __syncwarp();
+              stage_rows64_sw64(slot, lane, o);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&hmap, slot, q * 64 + half * 32, (int)((long long)g * a.rows_total + tile * TC_TM + quad * 32));
+                bulk_commit_group();
+              }
+              ++n_staged;
               // the ReLU mask of the same 32 values as one word: the data-gradient kernel reads 4 B instead of these 64 B
               uint32_t m = 0;
 #pragma unroll
@@ -469,6 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         rp ^= 1;
       }
     }
+    if (TRAIN && lane == 0) bulk_wait_group<0>();          // every staged slice has reached global memory before the CTA retires
   }
 
   tc_fence_before();
@@ -489,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 }
 
 template <int NPASS, int UVD, int CL, bool TRAIN = false>
-static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
+static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st, const CUtensorMap* hmap = nullptr) {
   static bool attr_set_dev[64] = {};   // cudaFuncSetAttribute is per device
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
@@ -517,7 +534,8 @@ static int launch_tc_impl(const TcArgs& a, long long n_tiles, cudaStream_t st) {
   at.val.clusterDim.z = 1;
   cfg.attrs = &at;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, mlp_tc_kernel<NPASS, UVD, CL, TRAIN>, a);
+  static const CUtensorMap no_map = {};
+  cudaLaunchKernelEx(&cfg, mlp_tc_kernel<NPASS, UVD, CL, TRAIN>, a, hmap ? *hmap : no_map);
   return check_launch(TRAIN ? "mlp_tc_kernel<train>" : "mlp_tc_kernel") ? 0 : 5;
 }
 
@@ -636,7 +654,9 @@ int launch_mlp_tc_train(const void* blob, const PointSrc& src, int n_frames, con
     set_error("mlp_tc_train: 4-tap live render (GRID_ENS4) or explicit rows, uv_dims = 2");
     return 2;
   }
-  return launch_tc_impl<1, 2, 1, true>(a, n_tiles, st);
+  CUtensorMap hmap;
+  if (!encode_2d(&hmap, save_h, 256, 8ull * (unsigned long long)a.rows_total, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return 6;
+  return launch_tc_impl<1, 2, 1, true>(a, n_tiles, st, &hmap);
 }
 
 }  // namespace s2l

@@ -194,6 +194,32 @@ __device__ __forceinline__ void st_rows64_paired(void* my_row, long long row_str
   st_global_v8(even_row + sec, s0);
   st_global_v8(even_row + row_stride_bytes + sec, s1);
 }
+// ---- asynchronous tile stores: a warp stages its [32 rows x 64 B] slice in shared memory (SWIZZLE_64B pattern: the 16-byte
+// chunk index of a row is XORed with bits 1..2 of the row — conflict-free for 64-byte rows) and ONE lane hands it to the TMA
+// engine.  The issuing warps never wait for the memory system: with plain st.global the epilogue warps — the critical path of
+// the training kernels — stalled on store back-pressure and the copy of h / dPre did not overlap the layer chain at all
+// (forward: 756 us of compute + 534 us of stores, measured with the stores compiled out).
+__device__ __forceinline__ void stage_rows64_sw64(uint8_t* slot, int lane, const uint32_t* o) {
+  const uint32_t base = smem_u32(slot) + (uint32_t)lane * 64u;
+  const uint32_t x = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+  for (uint32_t c = 0; c < 4; ++c)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((c ^ x) << 4)), "r"(o[4 * c]), "r"(o[4 * c + 1]), "r"(o[4 * c + 2]),
+                 "r"(o[4 * c + 3])
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(src_smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* r) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])

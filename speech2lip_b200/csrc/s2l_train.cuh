@@ -16,11 +16,41 @@
 //         (per frame for g = 0, 5);  the finalize step turns M0 / M5 / the per-frame sums into the gradients of
 //         W0, Wuv, W5a, Wuvs, fc_audio*, fc_time*, their biases and the latent.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include "s2l_common.cuh"
 #include "s2l_points.cuh"
 
 namespace s2l {
+
+// 2-D bf16 tensor map over a row-major [rows][cols] array, box = [box_rows][box_cols]
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline bool encode_2d(CUtensorMap* tm, void* base, unsigned long long cols, unsigned long long rows, unsigned box_cols, unsigned box_rows,
+                      CUtensorMapSwizzle sw) {
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+      set_error("training kernels: cuTensorMapEncodeTiled is not available from this driver");
+      return false;
+    }
+    enc = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("training kernels: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return false;
+  }
+  return true;
+}
 
 // Buffers of one training render (device pointers, caller-owned); rows are tile-major: row = tile * 128 + r.
 struct TrainBufs {

@@ -277,34 +277,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static bool encode_2d(CUtensorMap* tm, void* base, unsigned long long cols, unsigned long long rows, unsigned box_cols, unsigned box_rows,
-                      CUtensorMapSwizzle sw) {
-  static EncodeTiledFn enc = nullptr;
-  if (!enc) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
-      set_error("wgrad_tc: cuTensorMapEncodeTiled is not available from this driver");
-      return false;
-    }
-    enc = reinterpret_cast<EncodeTiledFn>(fn);
-  }
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {box_cols, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("wgrad_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return false;
-  }
-  return true;
-}
-
 int launch_wgrad_tc(const WgPlan& plan, const TrainBufs& B, cudaStream_t st) {
   if (plan.n_items() == 0 || B.rows_total == 0) return 0;
   WgArgs a{};
