@@ -498,23 +498,14 @@ def run_gpu_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, with_kernel_events):
-        tot = 0.0
-        ker = 0.0
-        if with_kernel_events:
-            lib.s2l_profile_enable(1)
-        for _ in range(steps):
-            flush.fill_(1)                                    # evict L2 between timed iterations (untimed)
-            e0, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e3.record()
-            e3.synchronize()
-            tot += e0.elapsed_time(e3)
-        if with_kernel_events:
-            ker = float(lib.s2l_profile_mlp_ms(None))
-            lib.s2l_profile_enable(0)
-        return tot, ker
+    def timed_once(fn):
+        flush.fill_(1)                                        # evict L2 between timed iterations (untimed)
+        e0, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e3.record()
+        e3.synchronize()
+        return e0.elapsed_time(e3)
 
     # ---- warm-up (untimed), then the timed region bracketed by barrier + synchronize
     for _ in range(max(a.warmup, 3)):
@@ -525,13 +516,23 @@ def run_gpu_arm(a):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    lib.s2l_launch_count(1)
     t_begin = time.perf_counter()
     barrier()
-    dev_ms, ker_ms = timed(step_device, a.steps, True)
-    barrier()
-    launches = lib.s2l_launch_count(0)
-    e2e_ms, _ = timed(step_e2e, a.steps, False)
+    # K device-resident steps and K end-to-end steps, INTERLEAVED: under the 1 kW power cap the SM clock sags over the first
+    # second of load, so two back-to-back loops would time the second leg at lower clocks than the first (that, not the
+    # copies, was most of the gap between `value` and `e2e`: the copies and host work cost 0.45 ms of a 48 ms step,
+    # tools/exp_e2e_breakdown.py).  Every step is bracketed by its own CUDA events; launches and the in-library kernel
+    # events are collected over the device-resident steps only.
+    dev_ms = e2e_ms = ker_ms = 0.0
+    launches = 0
+    for _ in range(a.steps):
+        lib.s2l_launch_count(1)
+        lib.s2l_profile_enable(1)
+        dev_ms += timed_once(step_device)
+        ker_ms += float(lib.s2l_profile_mlp_ms(None))
+        lib.s2l_profile_enable(0)
+        launches += int(lib.s2l_launch_count(0))
+        e2e_ms += timed_once(step_e2e)
     barrier()
     t_end = time.perf_counter()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
@@ -691,7 +692,7 @@ def run_gpu_arm(a):
             "dtype": {"bf16x3": "bf16x3-split (fp32 accumulate)", "bf16x1": "bf16", "fp32": "f32", "fp16f8": "fp16 + 2x fp8 corrections (fp32 accumulate)"}[a.precision], "data": "synthetic",
             "config": {"workload": workload_name(a), "mode": a.mode, "precision": a.precision, "tc_schedule": tc_sched,
                        "points_per_frame": P, "weights": "synthetic kaiming-normal ('trained-like'), seed 0",
-                       "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed",
+                       "l2": "flushed between timed steps (256 MiB fill, untimed); per-step CUDA events summed; device-resident and end-to-end steps interleaved",
                        "parallelism": "frames sharded across ranks, 1 NCCL weight broadcast at start, none during render"},
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(audio_h.numel() * 4 + index_h.numel() * 8 + (48 if vol else 0)),
