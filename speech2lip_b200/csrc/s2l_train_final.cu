@@ -175,14 +175,19 @@ __global__ void __launch_bounds__(256) wg_frame_terms_kernel(const uint8_t* __re
     return;
   }
   r -= nB;
-  if (r < nL) {
-    // d latent_f[k] = sum_j g0_f[j] Wa[j][k] + g5_f[j] Was[j][k]
-    const int f = (int)(r >> 6), k = (int)(r & 63);
+  if (r < nL * 32) {
+    // d latent_f[k] = sum_j g0_f[j] Wa[j][k] + g5_f[j] Was[j][k]: one warp per (f, k), lanes stride j (coalesced rows of the
+    // transposed weights; a thread per output walked them 1 KB apart), fixed-order shuffle reduction
+    const int lane = (int)(r & 31), o = (int)(r >> 5);
+    const int f = o >> 6, k = o & 63;
     const float* g0 = gvec(0, f);
     const float* g5 = gvec(1, f);
     float s = 0.f;
-    for (int j = 0; j < 256; ++j) s = fmaf(g0[j], C[C_FCA_WT + k * 256 + j], fmaf(g5[j], C[C_FCAS_WT + k * 256 + j], s));
-    G.d_latent[f * 64 + k] = s;
+#pragma unroll
+    for (int j = lane; j < 256; j += 32) s = fmaf(g0[j], C[C_FCA_WT + k * 256 + j], fmaf(g5[j], C[C_FCAS_WT + k * 256 + j], s));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) G.d_latent[f * 64 + k] = s;
   }
 }
 
@@ -305,7 +310,7 @@ static int train_backward(const void* blob, const PointSrc& src, int F, const Tr
     if (!check_launch("wg_chain_kernel")) return 5;
   }
   {
-    const long long n = 2ll * 256 * 64 + 2ll * 256 * 20 + 512 + (long long)F * 64;
+    const long long n = 2ll * 256 * 64 + 2ll * 256 * 20 + 512 + (long long)F * 64 * 32;
     wg_frame_terms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(blob), L, F, red, latent,
                                                                        reinterpret_cast<const long long*>(frame_idx), G);
     if (!check_launch("wg_frame_terms_kernel")) return 5;
