@@ -147,6 +147,8 @@ int32_t s2l_latent_bias_fwd(const void* blob, const float* latent, int64_t laten
 /* flag[0] (device int32) <- 1 if any of the n_rows rows of x (row stride row_stride floats) differs bitwise from row 0 in
  * columns [col0, col0+ncols), else 0.  Lets the drop-in detect inference.py's tiled inputs (inference.py:144: the same
  * audio window H*W times; :151: the same latent in every row) and run them once / through the tensor-core path. */
+int32_t s2l_rows_differ_or(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
+                           void* stream);   /* as s2l_rows_differ, but *flag is only ever set to 1, never cleared (sticky across calls) */
 int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
                         void* stream);
 

@@ -47,6 +47,7 @@ SYMBOLS = {
                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "s2l_latent_bias_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "s2l_rows_differ": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "s2l_rows_differ_or": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "s2l_audio_merge_auto_scratch_bytes": (C.c_size_t, []),
     "s2l_audio_merge_auto": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "s2l_rgb_forward_auto_scratch_bytes": (C.c_size_t, []),

@@ -352,12 +352,24 @@ __global__ void __launch_bounds__(256) rows_differ_kernel(const uint32_t* __rest
 }
 }  // namespace s2l
 
+static int32_t rows_differ_launch(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
+                                  void* stream, bool clear);
 extern "C" int32_t s2l_rows_differ(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
                                    void* stream) {
+  return rows_differ_launch(x, n_rows, row_stride, col0, ncols, flag, stream, true);
+}
+// the same compare, but the flag is only ever SET (never cleared): a sticky "some call had differing rows" indicator the host
+// reads once per training step instead of once per call
+extern "C" int32_t s2l_rows_differ_or(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
+                                      void* stream) {
+  return rows_differ_launch(x, n_rows, row_stride, col0, ncols, flag, stream, false);
+}
+static int32_t rows_differ_launch(const float* x, int64_t n_rows, int64_t row_stride, int32_t col0, int32_t ncols, int32_t* flag,
+                                  void* stream, bool clear) {
   if (!x || !flag) { set_error("s2l_rows_differ: null x/flag"); return 1; }
   if (n_rows < 0 || ncols < 0 || col0 < 0 || row_stride < col0 + ncols) { set_error("s2l_rows_differ: bad shape"); return 2; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
+  if (clear) cudaMemsetAsync(flag, 0, sizeof(int32_t), st);
   if (n_rows <= 1 || ncols == 0) return 0;
   const bool wide = (row_stride % 2 == 0) && (col0 % 2 == 0) && (ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const bool wide4 = (row_stride % 4 == 0) && (col0 % 4 == 0) && (ncols % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);

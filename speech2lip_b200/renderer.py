@@ -147,6 +147,17 @@ def rows_constant(x, col0, ncols):
     return int(flag.item()) == 0
 
 
+def rows_differ_or(x, col0, ncols, flag):
+    """Device-side, no host sync: sets the int32 device tensor `flag` to 1 when some row of x differs from row 0 in columns
+    [col0, col0+ncols); never clears it (a sticky indicator checked later)."""
+    lib = _cabi.lib()
+    x = _f32c(x, "x")
+    x2 = x.reshape(x.shape[0], -1)
+    with torch.cuda.device(x.device):
+        _cabi.check(lib.s2l_rows_differ_or(_ptr(x2), x2.shape[0], x2.shape[1], int(col0), int(ncols), _ptr(flag), _stream()),
+                    "s2l_rows_differ_or")
+
+
 def audio_merge_auto(w, audio, scratch):
     """TalkingFace.audio_merge_forward for a possibly tiled batch (inference.py:144), decided on the device: no host sync."""
     lib = _cabi.lib()

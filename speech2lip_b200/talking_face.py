@@ -208,6 +208,8 @@ class TalkingFace(nn.Module):
         key.append(vals[0].data_ptr())
         key.append(vals[-1].data_ptr())
         if self._packed is None or key != self._packed_key:
+            if self.__dict__.get("_tc_viol") is not None:
+                self.check_train_rows()               # once per optimizer step: the deferred precondition check of the bf16 per-call path
             if self._packed is None:
                 self._packed = R.PackedWeights(hp, self.uv_dims, self.output_ch)
             else:
@@ -253,7 +255,7 @@ class TalkingFace(nn.Module):
         if self._needs_grad(uv_audio_pts):
             x = uv_audio_pts
             if (self.train_precision == "bf16" and isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and self.uv_dims == 2
-                    and self.output_ch == 3 and x.shape[1] == 66 and x.shape[0] >= self.dropin_min_rows and R.rows_constant(x, 2, 64)):
+                    and self.output_ch == 3 and x.shape[1] == 66 and x.shape[0] >= self.dropin_min_rows and self._tc_rows_ok(x)):
                 # opt-in: the call's rows share one latent (training.py:216-233) -> bf16 tensor-core forward / backward
                 from .autograd import rgb_forward_train_tc
                 return rgb_forward_train_tc(self, x, time_pts)
@@ -271,6 +273,35 @@ class TalkingFace(nn.Module):
                                       self._dropin_scratch(x.device))
         t = None if time_pts is None else int(torch.as_tensor(time_pts).reshape(-1)[0].item())
         return R.rgb_forward_rows(self.packed_weights(), uv_audio_pts, t)
+
+    # ---- precondition of the opt-in bf16 per-call training path: every row of a call carries the same latent
+    _TC_SYNC_CALLS = int(os.environ.get("S2L_TC_SYNC_CALLS", "8"))       # (a huge value = always check synchronously)
+
+    def _tc_rows_ok(self, x):
+        """The first calls are checked synchronously (a caller that does not tile the latent is routed to the exact path and
+        never enters the tensor-core one).  After that the compare kernel only sets a sticky device flag — no host
+        synchronisation per call, which is what made the unmodified Trainer loop host-bound — and the flag is read once per
+        training step (check_train_rows, called when the packed weights are refreshed after an optimizer step)."""
+        n = self.__dict__.get("_tc_calls", 0)
+        self.__dict__["_tc_calls"] = n + 1
+        if n < self._TC_SYNC_CALLS:
+            return R.rows_constant(x, 2, 64)
+        viol = self.__dict__.get("_tc_viol")
+        if viol is None or viol.device != x.device:
+            viol = self.__dict__["_tc_viol"] = torch.zeros(1, dtype=torch.int32, device=x.device)
+        R.rows_differ_or(x, 2, 64, viol)
+        return True
+
+    def check_train_rows(self):
+        """Raises if any rgb_forward call since the last check violated the bf16 per-call path's precondition."""
+        viol = self.__dict__.get("_tc_viol")
+        if viol is not None and int(viol.item()) != 0:
+            viol.zero_()
+            self.__dict__["_tc_calls"] = 0
+            raise RuntimeError("speech2lip_b200: train_precision='bf16' — an rgb_forward call since the last check had rows with "
+                               "DIFFERENT latents; the tensor-core per-call path needs the tiled latent of Trainer.predict_lip_image "
+                               "(training.py:216-233).  The outputs and gradients of those calls are invalid: use train_precision='fp32' "
+                               "for such callers.")
 
     def _dropin_scratch(self, device):
         sc = self.__dict__.get("_dropin_sc")

@@ -7,6 +7,7 @@
       single-frame launches.
 Tolerances: per-tensor relative L2 error; bf16 has 8 significant bits (2^-9 = 2e-3 per rounding, ~10 roundings deep).
 """
+import json
 import math
 import os
 
@@ -345,3 +346,40 @@ def test_audio_net_backward_kernel_vs_oracle_autograd(S, layout):
             worst = max(worst, ((p.grad.cpu() - osd[k].grad).norm() / (osd[k].grad.norm() + 1e-30)).item())
     print("AudioNet backward kernel (%s): forward %.2e, worst relative gradient error %.2e" % (layout, e_fwd, worst))
     assert e_fwd < 1e-5 and worst < 1e-5
+
+
+def test_bf16_per_call_path_checks_its_precondition_without_a_sync_per_call(S):
+    """train_precision='bf16': after the first (synchronously checked) calls, rgb_forward only sets a sticky device flag when a
+    call's rows carry different latents; check_train_rows() — run once per optimizer step — raises.  Row-constant calls never
+    trip it, and their results equal the synchronously checked ones bit for bit."""
+    cfg = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "may_cfg.json")))
+    m = S.TalkingFace(device=dev(), cfg=cfg).to(dev()).train()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state_dict(0, "kaiming", 2, 3).items()}, strict=False)
+    m.train_precision = "bf16"
+    N = 2048
+    g = torch.Generator().manual_seed(4)
+    uv = torch.rand(N, 2, generator=g).to(dev())
+    lat = torch.randn(1, 64, generator=g).to(dev())
+    t = torch.tensor([3], device=dev())
+
+    def call(latents):
+        x = torch.cat([uv, latents], 1).requires_grad_(True)
+        out = m.rgb_forward(x, time_pts=t)
+        out.sum().backward()
+        return out.detach().clone()
+    first = call(lat.expand(N, -1))                       # synchronously checked
+    for _ in range(m._TC_SYNC_CALLS + 2):
+        again = call(lat.expand(N, -1))                   # from call 9 on: deferred check
+    assert torch.equal(first, again)
+    m.check_train_rows()                                  # nothing to report
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        call(lat.expand(N, -1))                           # the deferred path has no host synchronisation in the forward
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    bad = lat.expand(N, -1).clone()
+    bad[N // 2, 5] += 1.0
+    m.rgb_forward(torch.cat([uv, bad], 1).requires_grad_(True), time_pts=t)
+    with pytest.raises(RuntimeError, match="DIFFERENT latents"):
+        m.check_train_rows()
+    m.check_train_rows()                                  # the flag was cleared by the report
