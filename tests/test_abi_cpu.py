@@ -244,3 +244,17 @@ def test_render_lip_train_and_dropin_refuse_cpu_tensors():
             s2l.TalkingFace(device=torch.device("cpu"), cfg=cfg)
         finally:
             del os.environ["S2L_DROPIN_PRECISION"]
+
+
+def test_documents_only_cite_profile_files_that_exist():
+    """Every `profiles/<file>` (and `r2x_<file>` listed in profiles/README.md) the documents cite is committed."""
+    missing = []
+    for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", os.path.join("profiles", "README.md")):
+        text = open(os.path.join(ROOT, doc)).read()
+        names = set(re.findall(r"profiles/([A-Za-z0-9_.\-]+\.(?:md|json|csv|txt))", text))
+        if doc.endswith(os.path.join("profiles", "README.md")):
+            names |= set(re.findall(r"`(r[0-9][a-z]_[A-Za-z0-9_.\-]+\.(?:md|json|csv|txt))`", text))
+        for n in sorted(names):
+            if "*" not in n and not os.path.exists(os.path.join(ROOT, "profiles", n)):
+                missing.append((doc, n))
+    assert not missing, missing
