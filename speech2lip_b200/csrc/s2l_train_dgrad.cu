@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dgrad_tc_kernel(const __grid_co
               tc_fence_before();
               mbar_arrive(&epi_done[q]);                // released before the copy to global memory: the stores overlap the next MMAs
             }
+#ifndef S2L_DBG_DG_NOSTORE     // experiment: the chain without its copies to global memory (results are garbage, timing only)
             st_rows64_paired(drow + q * 64 + half * 32, 512, o, lane);
+#endif
           }
         }
         rp ^= 1;
